@@ -1,0 +1,147 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference under oracle/ref_shim.py.
+
+Run here (the container that has /root/reference):   python -m oracle.gen_golden [names...]
+The fixtures are what pins the oracle (oracle/mht_oracle.py) and, through it, the CUDA path.
+TEST INFRASTRUCTURE ONLY.
+
+Every fixture stores, per scan: the measurement array fed to the reference, the scan time, and
+for every live track after `Tracker.addMeasurementList` returned: Target.ID, the selected leaf's
+measurementNumber history over the whole track (helpFunctions.backtrackMeasurementNumbers),
+x_0, P_0, cumulativeNLLR, plus leaf counts, cluster count and the reference's stage timers.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+from oracle import ref_shim
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+T_RADAR = 2.5
+T0 = 1000.0
+
+
+def _scenario(name):
+    """(initial states (T,4), n_scans, radarRange, lambda_phi, N, P_d, seed)."""
+    rng = np.random.RandomState(99)
+    if name == "cfg1_crossing":
+        x0 = np.array([[-60.0, 1.0, 6.0, 0.0], [1.0, -60.0, 0.0, 6.0]])
+        return x0, 14, 161.6, 1e-4, 3, 0.9, 5446
+    if name == "cfg2_small":
+        return None, 10, 760.0, 1e-4, 4, 0.9, 1234, 20
+    if name == "cfg2":
+        return None, 8, 1702.0, 1e-4, 4, 0.9, 1234, 100
+    if name == "cfg3_head":
+        return None, 2, 1142.0, 1e-3, 6, 0.9, 1234, 1000
+    if name == "cfg3_scan3":
+        return None, 3, 1142.0, 1e-3, 6, 0.9, 1234, 1000
+    if name == "cfg5_small":
+        # 6 crossing pairs + 12 background targets, N=5: dense ILP compatibility rows
+        xs = []
+        for k in range(6):
+            c = rng.uniform(-500, 500, size=2)
+            v = 8.0
+            tc = 4 * T_RADAR                      # both reach c at scan 4
+            xs.append([c[0] - v * tc, c[1] + 3.0, v, 0.0])
+            xs.append([c[0] + 2.0, c[1] - v * tc, 0.0, v])
+        for k in range(12):
+            p = rng.uniform(-600, 600, size=2)
+            a = rng.uniform(0, 2 * np.pi)
+            xs.append([p[0], p[1], 5 * np.cos(a), 5 * np.sin(a)])
+        return np.array(xs), 10, 900.0, 1e-4, 5, 0.9, 77
+    raise KeyError(name)
+
+
+def run_reference(name):
+    ref_shim.install()
+    import pymht.utils.simulator as sim
+    import pymht.models.pv as pv
+    from pymht.utils.classDefinitions import SimTargetCartesian
+    import pymht.utils.helpFunctions as hpf
+
+    sc = _scenario(name)
+    x0, n_scans, R, lam, N, Pd, seed = sc[:7]
+    sim.seed_simulator(seed)
+    p0 = np.array([0.0, 0.0])
+    if x0 is None:
+        init = sim.generateInitialTargets(sc[7], p0, R, Pd, pv.sigmaQ_true)
+        for tgt in init:
+            tgt.time = T0
+    else:
+        init = [SimTargetCartesian(np.array(x, dtype=np.float32), T0, Pd, pv.sigmaQ_true) for x in x0]
+    simList = sim.simulateTargets(init, n_scans * T_RADAR, T_RADAR, pv)
+    scans = sim.simulateScans(simList, T_RADAR, pv.C_RADAR, pv.R_RADAR(pv.sigmaR_RADAR_true), lam, R, p0,
+                              shuffle=True, localClutter=False, globalClutter=True, preInitialized=True)
+    trk = ref_shim.make_reference_tracker(T_RADAR, lam, 1e-9, N=N, P_d=Pd)
+    trk.preInitialize(simList)
+    out = {"init_x": np.array([t.cartesianState() for t in simList[0]], dtype=np.float64),
+           "init_time": np.float64(T0), "n_scans": np.int64(len(scans)),
+           "params": np.array([T_RADAR, lam, 1e-9, N, Pd, 5.99, R])}
+    for k, scan in enumerate(scans):
+        t = time.time()
+        trk.addMeasurementList(scan)
+        wall = time.time() - t
+        nodes = list(trk.getTrackNodes())
+        hist = hpf.backtrackMeasurementNumbers(nodes)
+        width = max([len(h) for h in hist], default=0)
+        H = -np.ones((len(nodes), width), dtype=np.int64)
+        for i, h in enumerate(hist):
+            H[i, :len(h)] = h
+        pre = "s%d_" % k
+        out[pre + "z"] = np.asarray(scan.measurements, dtype=np.float32)
+        out[pre + "time"] = np.float64(scan.time)
+        out[pre + "ids"] = np.array([n.ID for n in nodes], dtype=np.int64)
+        out[pre + "hist"] = H
+        out[pre + "x"] = np.array([n.x_0 for n in nodes], dtype=np.float64).reshape(len(nodes), 4)
+        out[pre + "P"] = np.array([n.P_0 for n in nodes], dtype=np.float64).reshape(len(nodes), 4, 4)
+        out[pre + "cnllr"] = np.array([n.cumulativeNLLR for n in nodes], dtype=np.float64)
+        out[pre + "nleaves"] = np.array([len(t.getLeafNodes()) for t in trk.__targetList__], dtype=np.int64)
+        out[pre + "nclusters"] = np.int64(len(trk.__clusterList__))
+        out[pre + "n_ilp"] = np.int64(trk.nOptimSolved)
+        out[pre + "toc"] = np.array([trk.toc[s] for s in ("Process", "Cluster", "Optim", "Terminate", "N-Prune")])
+        print("%s scan %d: M=%d tracks=%d leaves=%d clusters=%d ilps=%d wall=%.2fs" % (
+            name, k + 1, len(scan.measurements), len(nodes), int(out[pre + "nleaves"].sum()),
+            len(trk.__clusterList__), trk.nOptimSolved, wall), flush=True)
+    return out
+
+
+def kalman_kat():
+    """Outputs of the reference's own kalman.py functions on seeded random leaves."""
+    ref_shim.install()
+    import pymht.utils.kalman as rk
+    import pymht.models.pv as pv
+    rng = np.random.RandomState(4242)
+    L, M = 48, 300
+    A, Q, C, R = pv.Phi(T_RADAR), pv.Q(T_RADAR), pv.C_RADAR, pv.R_RADAR()
+    x0 = np.concatenate([rng.uniform(-200, 200, (L, 2)), rng.uniform(-10, 10, (L, 2))], axis=1)
+    G = rng.normal(size=(L, 4, 4)) * np.array([2.0, 2.0, 1.0, 1.0])[None, :, None]
+    P0 = (np.matmul(G, G.transpose(0, 2, 1)) + np.diag([6.25, 6.25, 1.9, 1.9])).astype(np.float32)
+    P0[: L // 3] = pv.P0
+    z = (x0[rng.randint(0, L, M), :2] + x0[rng.randint(0, L, M), 2:] * T_RADAR * rng.uniform(0, 2, (M, 1))
+         + rng.normal(scale=6.0, size=(M, 2))).astype(np.float32)
+    x_bar, P_bar = rk.predict(A, Q, x0, P0)
+    z_hat, S, S_inv, K, P_hat = rk.precalc(C, R, x_bar, P_bar)
+    zt = rk.z_tilde(z, z_hat, L, 2)
+    d2 = rk.normalizedInnovationSquared(zt, S_inv)
+    gate = d2 <= 5.99
+    Pd, lam = 0.9, 1e-4 + 1e-9
+    pair_leaf, pair_meas = np.nonzero(gate)
+    nllr = np.concatenate([rk.nllr(lam, Pd, S[i], d2[i, gate[i]]) for i in range(L)])
+    xhat = np.concatenate([rk.numpyFilter(x_bar[i], K[i], zt[i, gate[i]]) for i in range(L)])
+    return dict(x0=x0, P0=P0, z=z, x_bar=x_bar, P_bar=P_bar, z_hat=z_hat, S=S, S_inv=S_inv, K=K, P_hat=P_hat,
+                d2=d2, pair_leaf=pair_leaf, pair_meas=pair_meas, nllr=nllr, xhat=xhat,
+                params=np.array([T_RADAR, lam, Pd, 5.99]))
+
+
+def main(argv):
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    names = argv or ["kalman_kat", "cfg1_crossing", "cfg2_small", "cfg5_small", "cfg2", "cfg3_head"]
+    for name in names:
+        data = kalman_kat() if name == "kalman_kat" else run_reference(name)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **data)
+        print("wrote", name)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
