@@ -1,0 +1,193 @@
+/*
+ * mht_b200.h -- C ABI of libmht_b200.so: the B200 (sm_100a) implementation of pyMHT's per-scan hot
+ * path.  Plain pointers and sizes only; no torch / C++ types.  The reference (erikliland/pyMHT) is
+ * pure Python with no FFI of its own, so each entry point below names the reference *method* whose
+ * body it replaces (file:line into the reference tree) -- the ctypes stubs a maintainer would add
+ * are shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns an int status: MHT_OK (0) or a negative MHT_E_* code; never throws;
+ *     mht_last_error() returns a human-readable message for the last failure on the calling thread.
+ *   - pointers named d_* are DEVICE pointers owned by the caller (e.g. torch.Tensor.data_ptr());
+ *     h_* are HOST pointers.  Nothing is allocated inside except by mht_forest_create().
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous on
+ *     that stream unless documented otherwise.
+ *   - dtype contract = what the reference holds: states, innovations, NIS, NLLR and
+ *     cumulative scores float64; Phi,Q,C,R and the covariance chain (P_bar,S,S^-1,K,P_hat) float32,
+ *     each product evaluated as an ascending-k fused-multiply-add chain (bit-identical to the
+ *     reference's NumPy/OpenBLAS sgemm on the authoring host).
+ */
+#ifndef MHT_B200_H
+#define MHT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MHT_OK 0
+#define MHT_E_INVALID (-1)    /* bad argument                                             */
+#define MHT_E_CUDA (-2)       /* CUDA runtime error (see mht_last_error)                  */
+#define MHT_E_CAPACITY (-3)   /* an output buffer / forest level is too small             */
+#define MHT_E_NODEVICE (-4)   /* no sm_100 device visible: there is NO cpu fallback       */
+#define MHT_E_NOTOPTIMAL (-5) /* association solved but optimality not certified          */
+
+#define MHT_MAX_WINDOW 16     /* max N-scan window + 1 (path planes per hypothesis)       */
+
+/* Linear-Gaussian model constants, row-major, float32 like reference pymht/models/pv.py:7-34. */
+typedef struct mht_model {
+    float A[16];       /* Phi(T)      pv.py:27-32  */
+    float Q[16];       /* Q(T)        pv.py:17-23  */
+    float C[8];        /* C_RADAR     pv.py:7-8    */
+    float R[4];        /* R_RADAR()   pv.py:25-26  */
+    double eta2;       /* gate        tracker.py:110 */
+    double lambda_ex;  /* lambda_phi + lambda_nu  tracker.py:107 */
+} mht_model;
+
+int mht_version(void);
+const char *mht_last_error(void);
+/* number of visible sm_100 devices (0 => every compute entry point returns MHT_E_NODEVICE). */
+int mht_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stateless operator: replaces the body of Tracker._processLeafNodes for ANY batch of leaves
+ * (reference pymht/tracker.py:383-398,804-889 = kalman.predict/precalc/z_tilde/
+ * normalizedInnovationSquared/numpyFilter/nllr, pymht/utils/kalman.py:14-101) plus the zero
+ * hypothesis score of Target.createZeroHypothesis (pymht/pyTarget.py:319-328).
+ *
+ * in : d_x0[L,4] f64, d_P0[L,16] f32, d_Pd[L] f64, d_cnllr[L] f64, d_z[M,2] f64
+ * out: d_x_bar[L,4] f64, d_P_bar[L,16] f32, d_P_hat[L,16] f32, d_miss_cnllr[L] f64,
+ *      d_pair_off[L+1] i32 (pairs of leaf l are [off[l], off[l+1]), ascending measurement index),
+ *      d_pair_meas[cap] i32 (0-based index), d_pair_cnllr[cap] f64 (parent cNLLR + NLLR),
+ *      d_pair_xhat[cap,4] f64, d_meas_used[M] u8 (feeds tracker.py:331-332,266)
+ * d_work: >= mht_gate_batch_workspace(L, M) bytes.  Returns MHT_E_CAPACITY if the pair count
+ * exceeds `cap` (d_pair_off[L] still holds the required count).  Synchronises the stream once
+ * (it has to read the pair count).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t mht_gate_batch_workspace(int64_t L, int64_t M);
+int mht_gate_batch(const mht_model *model, int64_t L, int64_t M, const double *d_x0, const float *d_P0,
+                   const double *d_Pd, const double *d_cnllr, const double *d_z, double *d_x_bar,
+                   float *d_P_bar, float *d_P_hat, double *d_miss_cnllr, int32_t *d_pair_off,
+                   int32_t *d_pair_meas, double *d_pair_cnllr, double *d_pair_xhat, int64_t cap,
+                   uint8_t *d_meas_used, void *d_work, void *stream);
+
+/* Same operator with HOST buffers (copies in, runs, copies out, synchronous): the form a
+ * reference-side ctypes stub in Tracker._processLeafNodes would call.  On MHT_E_CAPACITY
+ * h_pair_off[L] holds the required pair count. */
+int mht_gate_batch_host(const mht_model *model, int64_t L, int64_t M, const double *h_x0, const float *h_P0,
+                        const double *h_Pd, const double *h_cnllr, const double *h_z, double *h_x_bar,
+                        float *h_P_bar, float *h_P_hat, double *h_miss_cnllr, int32_t *h_pair_off,
+                        int32_t *h_pair_meas, double *h_pair_cnllr, double *h_pair_xhat, int64_t cap,
+                        uint8_t *h_meas_used);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stateless operators on an explicit column list (one column = one leaf hypothesis).
+ *
+ * mht_cluster: Tracker._findClustersFromSets (tracker.py:961-974).  Columns carry their tree and
+ * up to `width` measurement-row ids (row < 0 = unused slot).  out d_cluster_of_tree[T] = smallest
+ * tree index of the tree's connected component.
+ *
+ * mht_assoc_solve: the cluster loop of Tracker.addMeasurementList (tracker.py:228-236) =
+ * Target._selectBestHypothesis (pyTarget.py:446-459) for every singleton cluster and
+ * Tracker._solveOptimumAssociation/_solveBLP_OR_TOOLS (tracker.py:979-1217) for the rest, all
+ * clusters at once:   min sum c_j tau_j ; each tree exactly one column ; each row at most once.
+ * Columns of a tree must be contiguous (col_tree non-decreasing).  Lagrangian dual ascent on the
+ * row constraints + reduced-cost fixing + exact depth-first repair on the surviving columns.
+ * out d_selected_col[T] (column index per tree, -1 for trees without columns),
+ *     h_info[8] = {lower bound, objective, n_candidate_cols, n_components, bb_nodes, dual_iters,
+ *                  certified(1/0), max_component_trees}.
+ * Returns MHT_E_NOTOPTIMAL if the search budget ran out (d_selected_col is still feasible).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t mht_assoc_workspace(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t width);
+int mht_cluster(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t width, const int32_t *d_col_tree,
+                const int32_t *d_col_rows /* [width][n_cols] */, int32_t *d_cluster_of_tree, void *d_work,
+                void *stream);
+int mht_assoc_solve(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t width, const double *d_col_cost,
+                    const int32_t *d_col_tree, const int32_t *d_col_rows /* [width][n_cols] */,
+                    int32_t *d_selected_col, double *h_info, void *d_work, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident hypothesis forest: steps 1-3 + terminate + N-scan prune of
+ * Tracker.addMeasurementList (tracker.py:194-259) with the forest kept in HBM across scans.
+ * One forest per process / GPU; trees are independent so N ranks each own a shard of the trees.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mht_forest mht_forest; /* opaque */
+
+typedef struct mht_forest_config {
+    mht_model model;
+    int32_t n_scan_window;   /* N          tracker.py:112-114 */
+    int32_t max_trees;       /* tree slots                            */
+    int32_t max_meas;        /* measurements per scan capacity        */
+    int64_t max_nodes;       /* hypotheses per tree level capacity    */
+    int64_t max_parents;     /* live leaves entering a scan capacity  */
+    double default_Pd;       /* tracker.py:50 */
+    double score_upper;      /* tracker.py:115 */
+    double cnllr_upper;      /* tracker.py:116 */
+    double radar_range;      /* tracker.py:45  */
+    double position[2];      /* tracker.py:44  */
+    int32_t max_dual_iters;  /* Lagrangian iterations per scan        */
+    int32_t reserved;
+} mht_forest_config;
+
+/* Per-scan summary (host struct filled by mht_forest_scan). */
+typedef struct mht_scan_info {
+    int64_t n_parents;       /* live leaves gated this scan (L)            */
+    int64_t n_children;      /* hypotheses created (L + G)                 */
+    int64_t n_pairs;         /* gated (leaf,meas) pairs (G)                */
+    int32_t n_trees;         /* live trees before termination              */
+    int32_t n_clusters;      /* tracker.py:220                             */
+    int32_t n_multi_clusters;/* clusters with >1 tree (nOptimSolved)       */
+    int32_t n_dead;          /* tracks terminated this scan                */
+    int32_t dual_iters;
+    int32_t certified;       /* 1 = optimality certificate holds           */
+    int64_t n_candidates;    /* columns surviving reduced-cost fixing      */
+    int64_t bb_nodes;
+    double lower_bound;      /* sum over trees of cost, unscaled by N      */
+    double objective;
+    float ms_gate, ms_cluster, ms_assoc, ms_prune; /* CUDA-event stage times */
+} mht_scan_info;
+
+int mht_forest_create(const mht_forest_config *cfg, mht_forest **out);
+void mht_forest_destroy(mht_forest *f);
+/* bytes of device memory the forest holds */
+int64_t mht_forest_bytes(const mht_forest *f);
+
+/* Tracker.initiateTarget (tracker.py:147-160): new single-node tree; returns its slot in *slot. */
+int mht_forest_initiate(mht_forest *f, const double x0[4], const float P0[16], double Pd, int32_t *slot);
+
+/* One Tracker.addMeasurementList hot path.  h_z[M,2] f64 host (pinned or pageable), copied H2D on
+ * the forest's stream; returns after the per-track results are back on the host.
+ * h_meas_used[M] (may be NULL) receives the used-measurement mask of tracker.py:331-332. */
+int mht_forest_scan(mht_forest *f, int64_t M, const double *h_z, double scan_time, mht_scan_info *info,
+                    uint8_t *h_meas_used);
+
+/* Same, with the scan already resident in HBM (d_z[M,2] f64) and no host copies except the
+ * 64-byte status word: the kernel-only leg bench.py times as `value`. */
+int mht_forest_scan_device(mht_forest *f, int64_t M, const double *d_z, double scan_time, mht_scan_info *info);
+
+/* Selected hypothesis per live tree after the last scan (Tracker.getTrackNodes, tracker.py:976):
+ * h_slot[T] tree slot, h_x[T,4], h_P[T,16], h_cnllr[T], h_meas[T] (measurementNumber, 0 = miss),
+ * h_status[T] (0 active, 1 out-of-range, 2 too-low-score; dead tracks are reported once, in the scan
+ * that killed them, then dropped).  *n receives T. */
+int mht_forest_tracks(mht_forest *f, int32_t cap, int32_t *n, int32_t *h_slot, double *h_x, float *h_P,
+                      double *h_cnllr, int32_t *h_meas, int32_t *h_status);
+
+/* measurementNumber history of one track's selected leaf back to its initial node
+ * (helpFunctions.backtrackMeasurementNumbers, pymht/utils/helpFunctions.py:66-83), plus the states
+ * (h_x[n,4], h_cnllr[n], h_P[n,16]) along it, initial node included.  Oldest first. */
+int mht_forest_history(mht_forest *f, int32_t slot, int32_t cap, int32_t *n, int32_t *h_meas, double *h_x,
+                       double *h_cnllr, float *h_P);
+
+/* Smallest distance from (px,py) to any live leaf's position: the test of
+ * Target.haveNoNeightbours (pymht/pyTarget.py:181-189) used by Tracker.initiateTarget. */
+int mht_forest_min_leaf_distance(mht_forest *f, double px, double py, double *dist);
+
+/* Leaves of one tree in the reference's DFS order (Target.getLeafNodes, pyTarget.py:461-471). */
+int mht_forest_leaves(mht_forest *f, int32_t slot, int64_t cap, int64_t *n, double *h_x, double *h_cnllr,
+                      int32_t *h_meas);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MHT_B200_H */

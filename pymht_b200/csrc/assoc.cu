@@ -1,0 +1,992 @@
+// Association stage on device.
+//
+//   mht_cluster      = Tracker._findClustersFromSets            (reference pymht/tracker.py:961-974)
+//   mht_assoc_solve  = the cluster loop tracker.py:228-236: Target._selectBestHypothesis
+//                      (pymht/pyTarget.py:446-459) + _solveOptimumAssociation/_solveBLP_OR_TOOLS
+//                      (tracker.py:979-1217), every cluster at once.
+//
+// 0/1 program (tracker.py:1155-1217):  min sum_j c_j tau_j,  one column per tree (A2 tau = 1),
+// every measurement row used at most once (A1 tau <= 1).  Columns are leaves; a column's rows are
+// the <= N+1 measurements on its root->leaf path, so A1 is never materialised (the reference builds
+// it dense: 680 MB at 86k x 7.9k).
+//
+// Algorithm (LP-relaxation primal-dual + integer repair):
+//   1. union-find over (tree,row) incidences -> clusters (independent sub-problems).
+//   2. Lagrangian dual of the row constraints, L(u) = -sum u_r + sum_t min_j (c_j + sum_{r in j} u_r):
+//      projected subgradient ascent with a Polyak step PER CLUSTER; one streaming pass over the
+//      columns per iteration (reduced cost + per-tree argmin).  A cluster whose argmins are
+//      conflict-free and complementary is solved exactly (this covers every singleton cluster in
+//      the first iteration = _selectBestHypothesis, ties -> last leaf like the reference's '<=').
+//   3. primal: parallel greedy on reduced costs (bids on rows, lowest reduced cost wins).
+//   4. reduced-cost fixing: only columns with rc_j - min_t <= UB_c - L_c can be optimal; the
+//      survivors are split into connected components and each is searched exactly, depth first,
+//      with the Lagrangian bound.  A finished search certifies optimality.
+// Sums that steer the iteration are accumulated in 2^-34 fixed point so the result does not depend
+// on atomic ordering.
+#include "assoc.cuh"
+
+namespace mht {
+
+constexpr double kFix = 17179869184.0;  // 2^34
+constexpr int kPatience = 10;
+constexpr double kShrink = 0.7;
+constexpr int kMaxCandPerTree = 192;
+constexpr int kGreedyRounds = 40;
+constexpr int kGreedyEvery = 40;
+constexpr unsigned long long kKeyInf = ~0ull;
+
+__device__ __forceinline__ long long to_fix(double v) { return __double2ll_rn(v * kFix); }
+__device__ __forceinline__ double from_fix(long long v) { return (double)v / kFix; }
+
+__device__ __forceinline__ double col_cost(const ColView &c, int j, int t) {
+    return c.tree_base ? c.cost[j] - c.tree_base[t] : c.cost[j];
+}
+
+// ------------------------------------------------------------------------------------------------
+// union-find (link the larger root under the smaller: label = smallest tree index)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(int *uf, int x) {
+    int p = ((volatile int *)uf)[x];
+    while (p != x) {
+        const int gp = ((volatile int *)uf)[p];
+        if (gp != p) uf[x] = gp;  // path halving (benign race)
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+__device__ __forceinline__ void uf_union(int *uf, int a, int b) {
+    while (true) {
+        a = uf_find(uf, a);
+        b = uf_find(uf, b);
+        if (a == b) return;
+        if (a > b) {
+            const int t = a;
+            a = b;
+            b = t;
+        }
+        if (atomicCAS(&uf[b], b, a) == b) return;
+    }
+}
+
+__global__ void assoc_init_kernel(ColView c, AssocWork w, int *tstart, int *tend) {
+    const int T = c.n_trees, R = c.n_rows;
+    const int n = *c.n_ptr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max(max(T + 1, R), n); i += gridDim.x * blockDim.x) {
+        if (i < T) {
+            w.uf[i] = i;
+            w.tmin[i] = kKeyInf;
+            w.targ[i] = -1;
+            w.sel[i] = -1;
+            w.cl_best[i] = -1e300;
+            w.cl_ub[i] = 1e300;
+            w.cl_theta[i] = 1.0;
+            w.cl_step[i] = 0.0;
+            w.cl_stall[i] = 0;
+            w.cl_done[i] = 0;
+            w.cl_flag[i] = 0;
+        }
+        if (i <= T) w.cand_cnt[i] = 0;
+        if (i < R) {
+            w.row_owner[i] = -1;
+            w.u[i] = 0.0;
+            w.best_u[i] = 0.0;
+            w.usage[i] = 0;
+        }
+        if (i < kAssocInfo) w.info[i] = 0;
+        if (i == 0) {
+            *w.bb_nodes = 0ull;
+            w.objective[0] = w.objective[1] = 0.0;
+        }
+        if (i < n) {  // tree column ranges
+            const int t = c.tree[i];
+            if (i == 0 || c.tree[i - 1] != t) tstart[t] = i;
+            if (i == n - 1 || c.tree[i + 1] != t) tend[t] = i + 1;
+        }
+    }
+}
+
+__global__ void assoc_clear_ranges_kernel(int T, int *tstart, int *tend) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x) {
+        tstart[i] = -1;
+        tend[i] = -1;
+    }
+}
+
+__global__ void uf_union_cols_kernel(ColView c, int *uf, int *row_owner) {
+    const int n = *c.n_ptr;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int t = c.tree[j];
+        for (int k = 0; k < c.width; ++k) {
+            const int r = c.rows[(long long)k * c.stride + j];
+            if (r < 0) continue;
+            int o = row_owner[r];
+            if (o < 0) {
+                o = atomicCAS(&row_owner[r], -1, t);
+                if (o < 0) o = t;
+            }
+            if (o != t) uf_union(uf, t, o);
+        }
+    }
+}
+
+__global__ void uf_flatten_kernel(int T, int *uf) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) uf[t] = uf_find(uf, t);
+}
+
+// single CTA: cluster statistics (n clusters, clusters with > 1 tree); cl_nrm used as size scratch
+__global__ void __launch_bounds__(1024, 1)
+cluster_stats_kernel(int T, const int *uf, const int *tstart, int *cl_size, int *info) {
+    __shared__ int ncl, nmulti;
+    if (threadIdx.x == 0) ncl = nmulti = 0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) cl_size[t] = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x)
+        if (tstart[t] >= 0) atomicAdd(&cl_size[uf[t]], 1);
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x)
+        if (cl_size[t] > 0) {
+            atomicAdd(&ncl, 1);
+            if (cl_size[t] > 1) atomicAdd(&nmulti, 1);
+        }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        info[7] = ncl;
+        info[8] = nmulti;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dual ascent: column passes
+// ------------------------------------------------------------------------------------------------
+// min over runs of equal tree id inside a warp (columns are sorted by tree); returns true on the
+// first lane of each run, which then holds the run minimum.
+__device__ __forceinline__ bool warp_run_min(int t, unsigned long long &key) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long ok = __shfl_down_sync(0xffffffffu, key, o);
+        const int ot = __shfl_down_sync(0xffffffffu, t, o);
+        if (lane + o < 32 && ot == t && ok < key) key = ok;
+    }
+    const int pt = __shfl_up_sync(0xffffffffu, t, 1);
+    return lane == 0 || pt != t;
+}
+
+template <bool FORCE>
+__global__ void __launch_bounds__(256) dual_rc_kernel(ColView c, AssocWork w) {
+    if (!FORCE && w.info[0]) return;
+    const int n = *c.n_ptr;
+    const int nround = (n + 31) & ~31;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += gridDim.x * blockDim.x) {
+        int t = -1;
+        unsigned long long key = kKeyInf;
+        if (j < n) {
+            t = c.tree[j];
+            if (FORCE || !w.cl_done[w.uf[t]]) {
+                double v = col_cost(c, j, t);
+                for (int k = 0; k < c.width; ++k) {
+                    const int r = c.rows[(long long)k * c.stride + j];
+                    if (r >= 0) v += w.u[r];
+                }
+                w.rc[j] = v;
+                key = f64_key(v);
+            } else {
+                t = -1;
+            }
+        }
+        const bool head = warp_run_min(t, key);
+        if (head && t >= 0) atomicMin(&w.tmin[t], key);
+    }
+}
+
+template <bool FORCE>
+__global__ void __launch_bounds__(256) dual_arg_kernel(ColView c, AssocWork w) {
+    if (!FORCE && w.info[0]) return;
+    const int n = *c.n_ptr;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int t = c.tree[j];
+        if (!FORCE && w.cl_done[w.uf[t]]) continue;
+        if (f64_key(w.rc[j]) == w.tmin[t]) atomicMax(&w.targ[t], j);
+    }
+}
+
+// single CTA: subgradient, per-cluster Polyak step, bookkeeping (see file header)
+__global__ void __launch_bounds__(1024, 1) dual_update_kernel(ColView c, AssocWork w, const int *tstart) {
+    if (w.info[0]) return;
+    const int T = c.n_trees, R = c.n_rows;
+    __shared__ int open;
+    if (threadIdx.x == 0) open = 0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        w.cl_m[t] = 0;
+        w.cl_u[t] = 0;
+        w.cl_cost[t] = 0;
+        w.cl_nrm[t] = 0;
+        w.cl_flag[t] = 0;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        if (tstart[t] < 0) continue;
+        const int cl = w.uf[t];
+        if (w.cl_done[cl]) continue;
+        const int j = w.targ[t];
+        atomicAdd((unsigned long long *)&w.cl_m[cl], (unsigned long long)to_fix(key_f64(w.tmin[t])));
+        atomicAdd((unsigned long long *)&w.cl_cost[cl], (unsigned long long)to_fix(col_cost(c, j, t)));
+        for (int k = 0; k < c.width; ++k) {
+            const int r = c.rows[(long long)k * c.stride + j];
+            if (r >= 0) atomicAdd(&w.usage[r], 1);
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const int o = w.row_owner[r];
+        if (o < 0) continue;
+        const int cl = w.uf[o];
+        if (w.cl_done[cl]) continue;
+        int g = w.usage[r] - 1;
+        const double ur = w.u[r];
+        if (ur <= 0.0 && g < 0) g = 0;
+        w.usage[r] = g;
+        if (g) atomicAdd(&w.cl_nrm[cl], g * g);
+        if (ur > 0.0) atomicAdd((unsigned long long *)&w.cl_u[cl], (unsigned long long)to_fix(ur));
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        if (tstart[t] < 0 || w.uf[t] != t || w.cl_done[t]) continue;
+        const double L = from_fix(w.cl_m[t] - w.cl_u[t]);
+        const int nrm = w.cl_nrm[t];
+        if (nrm == 0) {  // conflict-free and complementary: argmins are optimal
+            w.cl_done[t] = 1;
+            w.cl_best[t] = L;
+            w.cl_ub[t] = from_fix(w.cl_cost[t]);
+            w.cl_flag[t] = 3;
+            w.cl_step[t] = 0.0;
+            continue;
+        }
+        if (L > w.cl_best[t] + 1e-12) {
+            w.cl_best[t] = L;
+            w.cl_flag[t] = 1;
+            w.cl_stall[t] = 0;
+        } else if (++w.cl_stall[t] >= kPatience) {
+            w.cl_theta[t] *= kShrink;
+            w.cl_stall[t] = 0;
+        }
+        if (w.cl_ub[t] - w.cl_best[t] < 1e-9) {
+            w.cl_done[t] = 1;
+            w.cl_step[t] = 0.0;
+        } else {
+            // no step before the first primal solution provides an upper bound
+            w.cl_step[t] = w.cl_ub[t] < 1e299 ? w.cl_theta[t] * (w.cl_ub[t] - L) / (double)nrm : 0.0;
+            atomicAdd(&open, 1);
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const int o = w.row_owner[r];
+        if (o < 0) continue;
+        const int cl = w.uf[o];
+        const int fl = w.cl_flag[cl];
+        if (fl & 1) w.best_u[r] = w.u[r];
+        if (!w.cl_done[cl]) w.u[r] = fmax(0.0, w.u[r] + w.cl_step[cl] * (double)w.usage[r]);
+        w.usage[r] = 0;
+    }
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        if (tstart[t] < 0) continue;
+        if (w.cl_flag[w.uf[t]] & 2) w.sel[t] = w.targ[t];
+        w.tmin[t] = kKeyInf;
+        w.targ[t] = -1;
+    }
+    if (threadIdx.x == 0) {
+        w.info[1] += 1;
+        if (open == 0) w.info[0] = 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// primal greedy in parallel rounds
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) greedy_init_kernel(ColView c, AssocWork w, const int *tstart) {
+    if (w.info[0]) return;
+    __shared__ int left;
+    if (threadIdx.x == 0) left = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < c.n_trees; t += blockDim.x) {
+        const bool part = tstart[t] >= 0 && !w.cl_done[w.uf[t]];
+        w.committed[t] = part ? 0 : 1;
+        w.prop_key[t] = kKeyInf;
+        w.prop_col[t] = -1;
+        w.sel_new[t] = -1;
+        if (part) atomicAdd(&left, 1);
+    }
+    for (int r = threadIdx.x; r < c.n_rows; r += blockDim.x) {
+        w.row_taken[r] = 0;
+        w.row_bid[r] = kKeyInf;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) w.info[2] = left;
+}
+
+__device__ __forceinline__ bool rows_free(const ColView &c, const int *taken, int j) {
+    for (int k = 0; k < c.width; ++k) {
+        const int r = c.rows[(long long)k * c.stride + j];
+        if (r >= 0 && taken[r]) return false;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(256) greedy_prop_kernel(ColView c, AssocWork w) {
+    if (w.info[0] || w.info[2] == 0) return;
+    const int n = *c.n_ptr;
+    const int nround = (n + 31) & ~31;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += gridDim.x * blockDim.x) {
+        int t = -1;
+        unsigned long long key = kKeyInf;
+        if (j < n) {
+            t = c.tree[j];
+            if (!w.committed[t] && rows_free(c, w.row_taken, j))
+                key = f64_key(w.rc[j]);
+            else
+                t = -1;
+        }
+        const bool head = warp_run_min(t, key);
+        if (head && t >= 0) atomicMin(&w.prop_key[t], key);
+    }
+}
+
+__global__ void __launch_bounds__(256) greedy_arg_kernel(ColView c, AssocWork w) {
+    if (w.info[0] || w.info[2] == 0) return;
+    const int n = *c.n_ptr;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int t = c.tree[j];
+        if (w.committed[t]) continue;
+        if (f64_key(w.rc[j]) == w.prop_key[t] && rows_free(c, w.row_taken, j)) atomicMax(&w.prop_col[t], j);
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1) greedy_commit_kernel(ColView c, AssocWork w) {
+    if (w.info[0] || w.info[2] == 0) return;
+    const int T = c.n_trees, R = c.n_rows;
+    __shared__ int left;
+    if (threadIdx.x == 0) left = 0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        if (w.committed[t]) continue;
+        const int j = w.prop_col[t];
+        if (j < 0) continue;
+        const unsigned long long bid = (w.prop_key[t] & ~0xFFFFFFull) | (unsigned long long)t;
+        for (int k = 0; k < c.width; ++k) {
+            const int r = c.rows[(long long)k * c.stride + j];
+            if (r >= 0) atomicMin(&w.row_bid[r], bid);
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        if (w.committed[t]) continue;
+        const int j = w.prop_col[t];
+        bool win = j >= 0;
+        if (win) {
+            const unsigned long long bid = (w.prop_key[t] & ~0xFFFFFFull) | (unsigned long long)t;
+            for (int k = 0; k < c.width; ++k) {
+                const int r = c.rows[(long long)k * c.stride + j];
+                if (r >= 0 && w.row_bid[r] != bid) win = false;
+            }
+        }
+        if (win) {
+            w.committed[t] = 1;
+            w.sel_new[t] = j;
+            for (int k = 0; k < c.width; ++k) {
+                const int r = c.rows[(long long)k * c.stride + j];
+                if (r >= 0) w.row_taken[r] = 1;
+            }
+        } else {
+            atomicAdd(&left, 1);
+            w.prop_key[t] = kKeyInf;
+            w.prop_col[t] = -1;
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) w.row_bid[r] = kKeyInf;
+    if (threadIdx.x == 0) w.info[2] = left;
+}
+
+// adopt the greedy solution for every cluster it improves
+__global__ void __launch_bounds__(1024, 1) greedy_finish_kernel(ColView c, AssocWork w, const int *tstart) {
+    if (w.info[0] || w.info[2] != 0) return;
+    const int T = c.n_trees;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        w.cl_cost[t] = 0;
+        w.cl_flag[t] = 0;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        if (tstart[t] < 0) continue;
+        const int cl = w.uf[t];
+        if (w.cl_done[cl]) continue;
+        atomicAdd((unsigned long long *)&w.cl_cost[cl], (unsigned long long)to_fix(col_cost(c, w.sel_new[t], t)));
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        if (tstart[t] < 0 || w.uf[t] != t || w.cl_done[t]) continue;
+        const double ub = from_fix(w.cl_cost[t]);
+        if (ub < w.cl_ub[t]) {
+            w.cl_ub[t] = ub;
+            w.cl_flag[t] = 4;
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        if (tstart[t] < 0) continue;
+        if (w.cl_flag[w.uf[t]] & 4) w.sel[t] = w.sel_new[t];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// final bound, candidates, components, exact search
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) final_prepare_kernel(ColView c, AssocWork w) {
+    for (int r = threadIdx.x; r < c.n_rows; r += blockDim.x) {
+        w.u[r] = w.best_u[r];
+        w.usage[r] = 0;
+        w.row_mark[r] = -1;
+        w.row_taken[r] = 0;
+    }
+    for (int t = threadIdx.x; t < c.n_trees; t += blockDim.x) {
+        w.tmin[t] = kKeyInf;
+        w.targ[t] = -1;
+    }
+    if (threadIdx.x == 0) w.info[0] = 0;  // re-arm the early-out word for the column passes
+}
+
+// per-cluster bound at best_u and gap -> cl_step; totals -> objective[0..1]
+__global__ void __launch_bounds__(1024, 1) final_bound_kernel(ColView c, AssocWork w, const int *tstart) {
+    const int T = c.n_trees, R = c.n_rows;
+    __shared__ long long lb, ob;
+    if (threadIdx.x == 0) lb = ob = 0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        w.cl_m[t] = 0;
+        w.cl_u[t] = 0;
+        w.cl_cost[t] = 0;
+        w.comp_uf[t] = t;
+        w.cand_fill[t] = 0;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        if (tstart[t] < 0) continue;
+        const int cl = w.uf[t];
+        if (w.sel[t] < 0) {  // no primal solution reached this tree (greedy ran out of rounds)
+            w.sel[t] = w.targ[t];
+            atomicAdd(&w.info[11], 1);
+        }
+        atomicAdd((unsigned long long *)&w.cl_m[cl], (unsigned long long)to_fix(key_f64(w.tmin[t])));
+        atomicAdd((unsigned long long *)&w.cl_cost[cl], (unsigned long long)to_fix(col_cost(c, w.sel[t], t)));
+    }
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const int o = w.row_owner[r];
+        if (o >= 0 && w.u[r] > 0.0)
+            atomicAdd((unsigned long long *)&w.cl_u[w.uf[o]], (unsigned long long)to_fix(w.u[r]));
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        if (tstart[t] < 0 || w.uf[t] != t) continue;
+        const double L = from_fix(w.cl_m[t] - w.cl_u[t]);
+        const double ub = from_fix(w.cl_cost[t]);
+        w.cl_best[t] = L;
+        w.cl_ub[t] = ub;
+        const double gap = ub - L;
+        w.cl_step[t] = gap;                     // candidate threshold of this cluster
+        w.cl_done[t] = gap <= 1e-9 ? 1 : 0;     // closed: incumbent proven optimal
+        atomicAdd((unsigned long long *)&lb, (unsigned long long)(w.cl_m[t] - w.cl_u[t]));
+        atomicAdd((unsigned long long *)&ob, (unsigned long long)w.cl_cost[t]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        w.objective[0] = from_fix(lb);
+        w.objective[1] = from_fix(ob);
+    }
+}
+
+__device__ __forceinline__ bool is_candidate(const ColView &c, const AssocWork &w, int j, int t) {
+    const int cl = w.uf[t];
+    if (w.cl_done[cl]) return false;
+    const double exc = w.rc[j] - key_f64(w.tmin[t]);
+    return exc <= w.cl_step[cl] + 1e-9 || j == w.sel[t];
+}
+
+__global__ void __launch_bounds__(256) cand_count_kernel(ColView c, AssocWork w) {
+    const int n = *c.n_ptr;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int t = c.tree[j];
+        if (is_candidate(c, w, j, t)) atomicAdd(&w.cand_cnt[t], 1);
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1) cand_scan_kernel(ColView c, AssocWork w) {
+    // T is small (<= ~10^4): serial chunks per thread + one block scan
+    const int T = c.n_trees;
+    __shared__ int part[1024];
+    __shared__ int over;
+    if (threadIdx.x == 0) over = 0;
+    const int per = (T + blockDim.x - 1) / blockDim.x;
+    const int lo = min(T, (int)threadIdx.x * per), hi = min(T, lo + per);
+    int s = 0;
+    for (int t = lo; t < hi; ++t) {
+        s += w.cand_cnt[t];
+        if (w.cand_cnt[t] > kMaxCandPerTree) over = 1;
+    }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int i = 0; i < (int)blockDim.x; ++i) {
+            const int v = part[i];
+            part[i] = acc;
+            acc += v;
+        }
+        w.info[3] = acc;
+        if (acc > w.cap_cand || over) w.info[6] = 1;
+    }
+    __syncthreads();
+    int acc = part[threadIdx.x];
+    for (int t = lo; t < hi; ++t) {
+        w.cand_off[t] = acc;
+        acc += w.cand_cnt[t];
+    }
+    if (hi == T && lo <= T) w.cand_off[T] = acc;
+}
+
+__global__ void __launch_bounds__(256) cand_fill_kernel(ColView c, AssocWork w) {
+    if (w.info[6]) return;
+    const int n = *c.n_ptr;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int t = c.tree[j];
+        if (is_candidate(c, w, j, t)) w.cand_col[w.cand_off[t] + atomicAdd(&w.cand_fill[t], 1)] = j;
+    }
+}
+
+// per tree: sort candidates by (excess, column); union trees that share a row among candidates
+__global__ void cand_sort_union_kernel(ColView c, AssocWork w) {
+    if (w.info[6]) return;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
+        const int cnt = w.cand_cnt[t];
+        if (cnt == 0) continue;
+        int *v = w.cand_col + w.cand_off[t];
+        for (int i = 1; i < cnt; ++i) {
+            const int key = v[i];
+            const double kr = w.rc[key];
+            int p = i - 1;
+            while (p >= 0 && (w.rc[v[p]] > kr || (w.rc[v[p]] == kr && v[p] > key))) {
+                v[p + 1] = v[p];
+                --p;
+            }
+            v[p + 1] = key;
+        }
+        for (int i = 0; i < cnt; ++i) {
+            const int j = v[i];
+            for (int k = 0; k < c.width; ++k) {
+                const int r = c.rows[(long long)k * c.stride + j];
+                if (r < 0) continue;
+                int o = w.row_mark[r];
+                if (o < 0) {
+                    o = atomicCAS(&w.row_mark[r], -1, t);
+                    if (o < 0) o = t;
+                }
+                if (o != t) uf_union(w.comp_uf, t, o);
+            }
+        }
+    }
+}
+
+// single CTA: group candidate trees by component; singletons are resolved here
+__global__ void __launch_bounds__(1024, 1) comp_build_kernel(ColView c, AssocWork w) {
+    if (w.info[6]) return;
+    const int T = c.n_trees;
+    __shared__ int ncomp, maxc;
+    if (threadIdx.x == 0) ncomp = maxc = 0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        w.comp_cnt[t] = 0;
+        if (w.cand_cnt[t] > 0) w.comp_uf[t] = uf_find(w.comp_uf, t);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x)
+        if (w.cand_cnt[t] > 0) atomicAdd(&w.comp_cnt[w.comp_uf[t]], 1);
+    __syncthreads();
+    // serial offsets (T small); components with >= 2 trees get a slot in comp_off order
+    if (threadIdx.x == 0) {
+        int acc = 0, k = 0;
+        for (int t = 0; t < T; ++t) {
+            const int n = w.comp_cnt[t];
+            w.cl_nrm[t] = -1;  // component slot of label t
+            if (n >= 2) {
+                w.comp_off[k] = acc;
+                w.cl_nrm[t] = k++;
+                acc += n;
+                maxc = max(maxc, n);
+            }
+        }
+        w.comp_off[k] = acc;
+        ncomp = k;
+        w.info[4] = k;
+        w.info[9] = maxc;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) w.cand_fill[t] = 0;  // reuse as per-component cursor
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        if (w.cand_cnt[t] == 0) continue;
+        const int lab = w.comp_uf[t];
+        const int slot = w.cl_nrm[lab];
+        if (slot >= 0) {
+            w.comp_trees[w.comp_off[slot] + atomicAdd(&w.cand_fill[lab], 1)] = t;
+        } else {  // alone: cheapest candidate wins
+            const int *v = w.cand_col + w.cand_off[t];
+            int best = v[0];
+            double bc = col_cost(c, best, t);
+            for (int i = 1; i < w.cand_cnt[t]; ++i) {
+                const double cc = col_cost(c, v[i], t);
+                if (cc < bc || (cc == bc && v[i] > best)) {
+                    bc = cc;
+                    best = v[i];
+                }
+            }
+            w.sel[t] = best;
+        }
+    }
+}
+
+// one CTA per component, thread 0 searches depth first with the Lagrangian bound
+__global__ void __launch_bounds__(32) branch_bound_kernel(ColView c, AssocWork w, int budget, double *fscratch) {
+    if (w.info[6]) return;
+    const int ncomp = w.info[4];
+    for (int comp = blockIdx.x; comp < ncomp; comp += gridDim.x) {
+        if (threadIdx.x != 0) continue;
+        const int off = w.comp_off[comp], k = w.comp_off[comp + 1] - off;
+        int *trees = w.comp_trees + off;
+        // deterministic order: fewest candidates first, then tree index
+        for (int i = 1; i < k; ++i) {
+            const int key = trees[i];
+            int p = i - 1;
+            while (p >= 0 && (w.cand_cnt[trees[p]] > w.cand_cnt[key] ||
+                              (w.cand_cnt[trees[p]] == w.cand_cnt[key] && trees[p] > key))) {
+                trees[p + 1] = trees[p];
+                --p;
+            }
+            trees[p + 1] = key;
+        }
+        int *pos = w.cand_stack + 3 * (long long)off, *chosen = pos + k, *bestsel = chosen + k;
+        double *exc_acc = fscratch + 2 * ((long long)off + comp), *cost_acc = exc_acc + (k + 1);
+        // component bound: sum of tree minima minus the multipliers of every row the candidates touch
+        double sum_m = 0.0, sum_u = 0.0, best = 0.0;
+        for (int i = 0; i < k; ++i) {
+            const int t = trees[i];
+            sum_m += key_f64(w.tmin[t]);
+            best += col_cost(c, w.sel[t], t);
+            bestsel[i] = w.sel[t];
+            const int *v = w.cand_col + w.cand_off[t];
+            for (int q = 0; q < w.cand_cnt[t]; ++q)
+                for (int kk = 0; kk < c.width; ++kk) {
+                    const int r = c.rows[(long long)kk * c.stride + v[q]];
+                    if (r >= 0 && w.usage[r] == 0) {
+                        w.usage[r] = 1;
+                        sum_u += w.u[r];
+                    }
+                }
+        }
+        const double Lcomp = sum_m - sum_u;
+        unsigned long long nodes = 0;
+        int depth = 0;
+        pos[0] = 0;
+        exc_acc[0] = 0.0;
+        cost_acc[0] = 0.0;
+        bool exhausted = false;
+        while (depth >= 0) {
+            const int t = trees[depth];
+            const int cnt = w.cand_cnt[t];
+            const int *v = w.cand_col + w.cand_off[t];
+            const double mt = key_f64(w.tmin[t]);
+            bool found = false;
+            while (pos[depth] < cnt) {
+                const int j = v[pos[depth]++];
+                const double e = fmax(0.0, w.rc[j] - mt);
+                if (Lcomp + exc_acc[depth] + e >= best - 1e-12) {
+                    pos[depth] = cnt;
+                    break;
+                }
+                if (!rows_free(c, w.row_taken, j)) continue;
+                for (int kk = 0; kk < c.width; ++kk) {
+                    const int r = c.rows[(long long)kk * c.stride + j];
+                    if (r >= 0) w.row_taken[r] = 1;
+                }
+                chosen[depth] = j;
+                exc_acc[depth + 1] = exc_acc[depth] + e;
+                cost_acc[depth + 1] = cost_acc[depth] + col_cost(c, j, t);
+                found = true;
+                break;
+            }
+            if (!found) {
+                --depth;
+                if (depth >= 0)
+                    for (int kk = 0; kk < c.width; ++kk) {
+                        const int r = c.rows[(long long)kk * c.stride + chosen[depth]];
+                        if (r >= 0) w.row_taken[r] = 0;
+                    }
+                continue;
+            }
+            if (++nodes > (unsigned long long)budget) {
+                exhausted = true;
+                break;
+            }
+            if (depth + 1 == k) {
+                if (cost_acc[k] < best - 1e-12) {
+                    best = cost_acc[k];
+                    for (int i = 0; i < k; ++i) bestsel[i] = chosen[i];
+                }
+                for (int kk = 0; kk < c.width; ++kk) {
+                    const int r = c.rows[(long long)kk * c.stride + chosen[depth]];
+                    if (r >= 0) w.row_taken[r] = 0;
+                }
+            } else {
+                ++depth;
+                pos[depth] = 0;
+            }
+        }
+        for (int i = 0; i < k; ++i) w.sel[trees[i]] = bestsel[i];
+        atomicAdd(w.bb_nodes, nodes);
+        if (exhausted) atomicAdd(&w.info[5], 1);
+    }
+}
+
+// single CTA: final objective and certificate
+__global__ void __launch_bounds__(1024, 1) final_objective_kernel(ColView c, AssocWork w, const int *tstart) {
+    __shared__ long long ob;
+    if (threadIdx.x == 0) ob = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < c.n_trees; t += blockDim.x)
+        if (tstart[t] >= 0)
+            atomicAdd((unsigned long long *)&ob, (unsigned long long)to_fix(col_cost(c, w.sel[t], t)));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        w.objective[1] = from_fix(ob);
+        w.info[10] = (w.info[5] == 0 && w.info[6] == 0 && w.info[11] == 0) ? 1 : 0;  // certified
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static inline int64_t al(int64_t b) { return (b + 255) / 256 * 256; }
+
+struct Carver {
+    char *p;
+    int64_t used = 0;
+    template <class T> T *take(int64_t n) {
+        T *r = p ? (T *)(p + used) : nullptr;
+        used += al(n * (int64_t)sizeof(T));
+        return r;
+    }
+};
+
+static int64_t carve_all(Carver &cv, int64_t cap_cols, int64_t T, int64_t R, int64_t cap_cand, AssocWork *w,
+                         int **tstart, int **tend, double **fscratch) {
+    AssocWork d;
+    d.rc = cv.take<double>(cap_cols);
+    d.tmin = cv.take<unsigned long long>(T);
+    d.targ = cv.take<int>(T);
+    d.uf = cv.take<int>(T);
+    d.sel = cv.take<int>(T);
+    d.sel_new = cv.take<int>(T);
+    d.committed = cv.take<int>(T);
+    d.prop_key = cv.take<unsigned long long>(T);
+    d.prop_col = cv.take<int>(T);
+    d.cl_m = cv.take<long long>(T);
+    d.cl_u = cv.take<long long>(T);
+    d.cl_cost = cv.take<long long>(T);
+    d.cl_nrm = cv.take<int>(T);
+    d.cl_best = cv.take<double>(T);
+    d.cl_ub = cv.take<double>(T);
+    d.cl_theta = cv.take<double>(T);
+    d.cl_step = cv.take<double>(T);
+    d.cl_stall = cv.take<int>(T);
+    d.cl_done = cv.take<int>(T);
+    d.cl_flag = cv.take<int>(T);
+    d.cand_cnt = cv.take<int>(T + 1);
+    d.cand_off = cv.take<int>(T + 1);
+    d.cand_fill = cv.take<int>(T + 1);
+    d.comp_uf = cv.take<int>(T);
+    d.comp_trees = cv.take<int>(T);
+    d.comp_off = cv.take<int>(T + 1);
+    d.comp_cnt = cv.take<int>(T);
+    d.row_owner = cv.take<int>(R);
+    d.u = cv.take<double>(R);
+    d.best_u = cv.take<double>(R);
+    d.usage = cv.take<int>(R);
+    d.row_bid = cv.take<unsigned long long>(R);
+    d.row_taken = cv.take<int>(R);
+    d.row_mark = cv.take<int>(R);
+    d.cand_col = cv.take<int>(cap_cand);
+    d.cand_stack = cv.take<int>(3 * T + 8);
+    d.cap_cand = cap_cand;
+    d.info = cv.take<int>(kAssocInfo);
+    d.bb_nodes = cv.take<unsigned long long>(1);
+    d.objective = cv.take<double>(2);
+    int *ts = cv.take<int>(T), *te = cv.take<int>(T);
+    double *fs = cv.take<double>(4 * T + 8);
+    if (w) *w = d;
+    if (tstart) *tstart = ts;
+    if (tend) *tend = te;
+    if (fscratch) *fscratch = fs;
+    return cv.used;
+}
+
+int64_t assoc_workspace_bytes(int64_t cap_cols, int64_t T, int64_t R, int64_t cap_cand) {
+    Carver cv{nullptr};
+    return carve_all(cv, cap_cols, T, R, cap_cand, nullptr, nullptr, nullptr, nullptr) + 256;
+}
+
+static thread_local int *g_tstart, *g_tend;
+static thread_local double *g_fscratch;
+
+void assoc_carve(void *d_work, int64_t cap_cols, int64_t T, int64_t R, int64_t cap_cand, AssocWork *w) {
+    Carver cv{(char *)d_work};
+    carve_all(cv, cap_cols, T, R, cap_cand, w, &g_tstart, &g_tend, &g_fscratch);
+}
+
+static int cluster_phase(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s) {
+    const int T = c.n_trees;
+    assoc_clear_ranges_kernel<<<(T + 255) / 256, 256, 0, s>>>(T, g_tstart, g_tend);
+    assoc_init_kernel<<<grid_dim, 256, 0, s>>>(c, w, g_tstart, g_tend);
+    uf_union_cols_kernel<<<grid_dim, 256, 0, s>>>(c, w.uf, w.row_owner);
+    uf_flatten_kernel<<<(T + 255) / 256, 256, 0, s>>>(T, w.uf);
+    cluster_stats_kernel<<<1, 1024, 0, s>>>(T, w.uf, g_tstart, w.cl_nrm, w.info);
+    MHT_CUDA(cudaGetLastError());
+    return MHT_OK;
+}
+
+int assoc_cluster(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s) {
+    return cluster_phase(c, w, grid_dim, s);
+}
+
+static void greedy_pass(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s) {
+    greedy_init_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
+    for (int r = 0; r < kGreedyRounds; ++r) {
+        greedy_prop_kernel<<<grid_dim, 256, 0, s>>>(c, w);
+        greedy_arg_kernel<<<grid_dim, 256, 0, s>>>(c, w);
+        greedy_commit_kernel<<<1, 1024, 0, s>>>(c, w);
+    }
+    greedy_finish_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
+}
+
+int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, int grid_dim, cudaStream_t s,
+                cudaEvent_t after_cluster) {
+    if (int rc = cluster_phase(c, w, grid_dim, s)) return rc;
+    if (after_cluster) MHT_CUDA(cudaEventRecord(after_cluster, s));
+    // iteration 0 settles every conflict-free cluster (all singletons) exactly
+    dual_rc_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
+    dual_arg_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
+    dual_update_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
+    for (int it = 0; it < max_iters; ++it) {
+        if (it % kGreedyEvery == 0) {
+            dual_rc_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);  // rc at the current multipliers
+            greedy_pass(c, w, grid_dim, s);
+            // dual_rc left tmin populated; dual_update below consumes a fresh pass anyway
+        }
+        dual_rc_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
+        dual_arg_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
+        dual_update_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
+    }
+    MHT_CUDA(cudaGetLastError());
+    // final multipliers -> reduced costs, bound, candidates, exact repair
+    final_prepare_kernel<<<1, 1024, 0, s>>>(c, w);
+    dual_rc_kernel<true><<<grid_dim, 256, 0, s>>>(c, w);
+    dual_arg_kernel<true><<<grid_dim, 256, 0, s>>>(c, w);
+    final_bound_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
+    cand_count_kernel<<<grid_dim, 256, 0, s>>>(c, w);
+    cand_scan_kernel<<<1, 1024, 0, s>>>(c, w);
+    cand_fill_kernel<<<grid_dim, 256, 0, s>>>(c, w);
+    cand_sort_union_kernel<<<(c.n_trees + 127) / 128, 128, 0, s>>>(c, w);
+    comp_build_kernel<<<1, 1024, 0, s>>>(c, w);
+    branch_bound_kernel<<<kSMs * 4, 32, 0, s>>>(c, w, bb_budget, g_fscratch);
+    final_objective_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
+    MHT_CUDA(cudaGetLastError());
+    return MHT_OK;
+}
+
+}  // namespace mht
+
+using namespace mht;
+
+extern "C" int64_t mht_assoc_workspace(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t width) {
+    (void)width;
+    return assoc_workspace_bytes(n_cols, n_trees, n_rows, n_cols) + 256;
+}
+
+static int make_view(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t width, const double *d_cost,
+                     const int32_t *d_tree, const int32_t *d_rows, void *d_work, ColView *c, AssocWork *w,
+                     cudaStream_t s) {
+    if (n_cols < 0 || n_cols > 0x7ffffff0ll || n_trees <= 0 || n_trees >= (1 << 24) || n_rows < 0 ||
+        n_rows > 0x7ffffff0ll || width < 0 || width > MHT_MAX_WINDOW || !d_work) {
+        set_error("assoc: invalid argument (n_cols=%lld n_trees=%lld n_rows=%lld width=%d)", (long long)n_cols,
+                  (long long)n_trees, (long long)n_rows, width);
+        return MHT_E_INVALID;
+    }
+    int *n_dev = (int *)d_work;
+    const int n32 = (int)n_cols;
+    MHT_CUDA(cudaMemcpyAsync(n_dev, &n32, sizeof(int), cudaMemcpyHostToDevice, s));
+    assoc_carve((char *)d_work + 256, n_cols, n_trees, n_rows, n_cols, w);
+    c->n_ptr = n_dev;
+    c->cost = d_cost;
+    c->tree_base = nullptr;
+    c->tree = d_tree;
+    c->rows = d_rows;
+    c->stride = n_cols;
+    c->width = width;
+    c->n_trees = (int)n_trees;
+    c->n_rows = (int)(n_rows ? n_rows : 1);
+    return MHT_OK;
+}
+
+extern "C" int mht_cluster(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t width, const int32_t *d_col_tree,
+                           const int32_t *d_col_rows, int32_t *d_cluster_of_tree, void *d_work, void *stream) {
+    if (int rc = check_device()) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    ColView c;
+    AssocWork w;
+    if (int rc = make_view(n_cols, n_trees, n_rows, width, nullptr, d_col_tree, d_col_rows, d_work, &c, &w, s))
+        return rc;
+    if (int rc = assoc_cluster(c, w, kSMs * 4, s)) return rc;
+    MHT_CUDA(cudaMemcpyAsync(d_cluster_of_tree, w.uf, n_trees * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    return MHT_OK;
+}
+
+extern "C" int mht_assoc_solve(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t width,
+                               const double *d_col_cost, const int32_t *d_col_tree, const int32_t *d_col_rows,
+                               int32_t *d_selected_col, double *h_info, void *d_work, void *stream) {
+    if (int rc = check_device()) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    ColView c;
+    AssocWork w;
+    if (int rc = make_view(n_cols, n_trees, n_rows, width, d_col_cost, d_col_tree, d_col_rows, d_work, &c, &w, s))
+        return rc;
+    if (int rc = assoc_solve(c, w, 200, 2000000, kSMs * 4, s)) return rc;
+    MHT_CUDA(cudaMemcpyAsync(d_selected_col, w.sel, n_trees * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    int info[kAssocInfo];
+    double obj[2];
+    unsigned long long nodes;
+    MHT_CUDA(cudaMemcpyAsync(info, w.info, sizeof(info), cudaMemcpyDeviceToHost, s));
+    MHT_CUDA(cudaMemcpyAsync(obj, w.objective, sizeof(obj), cudaMemcpyDeviceToHost, s));
+    MHT_CUDA(cudaMemcpyAsync(&nodes, w.bb_nodes, sizeof(nodes), cudaMemcpyDeviceToHost, s));
+    MHT_CUDA(cudaStreamSynchronize(s));
+    if (h_info) {
+        h_info[0] = obj[0];
+        h_info[1] = obj[1];
+        h_info[2] = info[3];
+        h_info[3] = info[4];
+        h_info[4] = (double)nodes;
+        h_info[5] = info[1];
+        h_info[6] = info[10];
+        h_info[7] = info[9];
+    }
+    if (!info[10]) {
+        set_error("mht_assoc_solve: optimality not certified (search budget or candidate capacity exhausted)");
+        return MHT_E_NOTOPTIMAL;
+    }
+    return MHT_OK;
+}

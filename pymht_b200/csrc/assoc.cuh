@@ -1,0 +1,67 @@
+// Association stage (cluster + global-hypothesis 0/1 program) shared between the stateless
+// operators and the forest.  See assoc.cu for the algorithm.
+#pragma once
+#include "common.cuh"
+
+namespace mht {
+
+constexpr int kAssocInfo = 16;  // ints in AssocWork::info
+
+// Column view: one column = one leaf hypothesis.  Columns of a tree are contiguous.
+struct ColView {
+    const int *n_ptr;          // device scalar: number of columns
+    const double *cost;        // [n]   (cumulative NLLR for the forest)
+    const double *tree_base;   // [T] or null: cost_j := cost[j] - tree_base[tree[j]]
+    const int *tree;           // [n] non-decreasing
+    const int *rows;           // [width][stride]  row id or <0
+    long long stride;
+    int width;
+    int n_trees;
+    int n_rows;
+};
+
+struct AssocWork {
+    // per column
+    double *rc;                // [cap_cols]
+    // per tree
+    unsigned long long *tmin;  // ordered key of min reduced cost
+    int *targ;                 // argmin column (ties -> last)
+    int *uf;                   // union-find parent -> cluster label (smallest tree index)
+    int *sel;                  // incumbent column per tree
+    int *sel_new;              // greedy scratch
+    int *committed;
+    unsigned long long *prop_key;
+    int *prop_col;
+    long long *cl_m, *cl_u, *cl_cost;   // fixed-point per-cluster sums (indexed by label)
+    int *cl_nrm;
+    double *cl_best, *cl_ub, *cl_theta, *cl_step;
+    int *cl_stall, *cl_done, *cl_flag;
+    int *cand_cnt, *cand_off, *cand_fill;   // [T+1]
+    int *comp_uf, *comp_trees, *comp_off, *comp_cnt;  // candidate components
+    // per row
+    int *row_owner;
+    double *u, *best_u;
+    int *usage;
+    unsigned long long *row_bid;
+    int *row_taken;
+    int *row_mark;
+    // candidates
+    int *cand_col;             // [cap_cand]
+    int *cand_stack;           // [T] DFS cursors, [T] order etc. carved by the kernel
+    long long cap_cand;
+    // device status words
+    int *info;                 // [kAssocInfo]: 0 all_done, 1 iters, 2 greedy_left, 3 n_cand, 4 n_comp,
+                               // 5 uncertified, 6 cand_overflow, 7 n_clusters, 8 n_multi, 9 max_comp
+    unsigned long long *bb_nodes;
+    double *objective;         // [2]: lower bound, objective
+};
+
+int64_t assoc_workspace_bytes(int64_t cap_cols, int64_t n_trees, int64_t n_rows, int64_t cap_cand);
+void assoc_carve(void *d_work, int64_t cap_cols, int64_t n_trees, int64_t n_rows, int64_t cap_cand, AssocWork *w);
+// cluster labels only (uf[t] = smallest tree index of the component); async
+int assoc_cluster(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s);
+// full solve; async; results in w.sel / w.info / w.objective
+int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, int grid_dim, cudaStream_t s,
+                cudaEvent_t after_cluster = nullptr);
+
+}  // namespace mht

@@ -1,0 +1,294 @@
+"""`Tracker` with the reference's public surface (pymht/tracker.py:39-307) whose per-scan hot path
+-- grow every track tree (gate + NLLR), cluster, maximise the global hypothesis, terminate,
+N-scan prune -- runs on a B200 through libmht_b200 (include/mht_b200.h).
+
+Replaced reference code: tracker.py:194-259 (steps 1-3, 6 and the N-scan prune of
+addMeasurementList), i.e. _growTarget/_processLeafNodes (:309-351,:383-398,:804-889),
+_findClustersFromSets (:961-974), _solveOptimumAssociation/_solveBLP_OR_TOOLS (:979-1217),
+__analyzeTrackTermination/_terminateTracks (:891-916,:353-381), _nScanPruning (:1219-1231).
+Kept call-compatible: __init__ kwargs, preInitialize, initiateTarget, addMeasurementList,
+getTrackNodes, runtimeLog/toc keys, getRuntimeAverage.
+Out of scope (fail loudly): AIS fusion, plotting, XML export, dynamicWindow, pruneSimilar.
+The M-of-N initiator is out of scope: `self.initiator` defaults to a null object; any object with
+processMeasurements(unusedRadar, unusedAis) -> [Target] can be plugged in (tracker.py:266-277).
+"""
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _lib
+from .pyTarget import Target, STATUS_TAGS, preinitializedTag, backtrackMeasurementNumbers  # noqa: F401
+from .utils.classDefinitions import AisMessageList
+
+
+class NullInitiator:
+    def processMeasurements(self, unusedRadarMeasurements, unusedAisMeasurements=None):
+        return []
+
+
+class Tracker:
+    def __init__(self, model, radarPeriod, lambda_phi, lambda_nu, **kwargs):
+        self.position = np.asarray(kwargs.get("position", np.array([0.0, 0.0])), dtype=np.float64)
+        self.radarRange = kwargs.get("radarRange", float("inf"))
+        self.radarPeriod = radarPeriod
+        self.default_P_d = kwargs.get("P_d", 0.8)
+        assert 0 < self.default_P_d < 1, "Invalid P_d"
+        self.model = model
+        self.A = model.Phi(radarPeriod)
+        self.C = model.C_RADAR
+        self.P_0 = model.P0
+        self.R_RADAR = model.R_RADAR()
+        self.Q = model.Q(radarPeriod)
+        self.mergeThreshold = 4 * (model.sigmaR_RADAR_tracker ** 2)
+        self.initiator = NullInitiator()
+
+        self.__targetList__ = []            # root views, one per live track
+        self.__targetWindowSize__ = []
+        self.__scanHistory__ = []
+        self.__trackNodes__ = np.empty(0, dtype=np.dtype(object))
+        self.__terminatedTargets__ = []
+        self.__clusterList__ = []
+        self.__aisHistory__ = []
+        self.trackIdCounter = 0
+        self.runtimeLog = {k: [] for k in ("Total", "Process", "Cluster", "Optim", "ILP-Prune", "DynN",
+                                           "N-Prune", "Terminate", "Init")}
+        self.tic, self.toc = {}, {}
+        self.nOptimSolved = 0
+        self.scanInfo = []                  # mht_scan_info dict per scan
+
+        self.lambda_phi, self.lambda_nu = lambda_phi, lambda_nu
+        self.lambda_ex = lambda_phi + lambda_nu
+        self.eta2 = kwargs.get("eta2", 5.99)
+        N = int(kwargs.get("N", 5))
+        self.N_max = self.N = N
+        self.scoreUpperLimit = -np.log(1 - self.default_P_d) * 0.8
+        self.clnnrUpperLimit = 3.0
+        if kwargs.get("pruneSimilar", False):
+            raise NotImplementedError("pruneSimilar is outside the accelerated path")
+
+        # device forest capacities (HBM): hypotheses per level / live leaves per scan
+        self.maxTargets = int(kwargs.get("maxTargets", 4096))
+        self.maxMeasurements = int(kwargs.get("maxMeasurements", 65536))
+        self.maxNodes = int(kwargs.get("maxNodes", 1 << 22))
+        self.maxParents = int(kwargs.get("maxParents", max(1 << 16, self.maxNodes // 3)))
+        self.maxDualIterations = int(kwargs.get("maxDualIterations", 120))
+        self._lib = _lib.load()
+        self._forest = None
+        self._slots = []                    # forest slot of each live track (list order = reference order)
+        self._slot_info = {}                # slot -> dict(ID, time0, x0, P0, P_d)
+        self._create_forest()
+
+    # ------------------------------------------------------------------------------------------
+    def _create_forest(self):
+        cfg = _lib.ForestConfig()
+        cfg.model = _lib.Model.from_arrays(self.A, self.Q, self.C, self.R_RADAR, self.eta2, self.lambda_ex)
+        cfg.n_scan_window = self.N
+        cfg.max_trees, cfg.max_meas = self.maxTargets, self.maxMeasurements
+        cfg.max_nodes, cfg.max_parents = self.maxNodes, self.maxParents
+        cfg.default_Pd = self.default_P_d
+        cfg.score_upper, cfg.cnllr_upper = float(self.scoreUpperLimit), float(self.clnnrUpperLimit)
+        cfg.radar_range = float(self.radarRange) if np.isfinite(self.radarRange) else 1e300
+        cfg.position[0], cfg.position[1] = float(self.position[0]), float(self.position[1])
+        cfg.max_dual_iters = self.maxDualIterations
+        handle = C.c_void_p()
+        _lib.check(self._lib.mht_forest_create(C.byref(cfg), C.byref(handle)))
+        self._forest = handle
+
+    def close(self):
+        if self._forest is not None:
+            self._lib.mht_forest_destroy(self._forest)
+            self._forest = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def deviceBytes(self):
+        return int(self._lib.mht_forest_bytes(self._forest))
+
+    # ------------------------------------------------------------------------------------------
+    def preInitialize(self, simList):
+        """Seed one track per ground-truth target of simList[0] (tracker.py:139-145)."""
+        for initialTarget in simList[0]:
+            self.initiateTarget(Target(initialTarget.time, None, np.asarray(initialTarget.cartesianState(), dtype=np.float64),
+                                       self.P_0, status=preinitializedTag))
+
+    def initiateTarget(self, newTarget):
+        """tracker.py:147-160: accept the target unless a live leaf is closer than mergeThreshold."""
+        if self.mergeThreshold > 0 and len(self._slots) > 0:
+            dist = C.c_double()
+            _lib.check(self._lib.mht_forest_min_leaf_distance(self._forest, float(newTarget.x_0[0]),
+                                                              float(newTarget.x_0[1]), C.byref(dist)))
+            if dist.value < self.mergeThreshold:
+                return
+        x0 = np.ascontiguousarray(newTarget.x_0, dtype=np.float64)
+        P0 = np.ascontiguousarray(newTarget.P_0, dtype=np.float32)
+        slot = C.c_int32()
+        _lib.check(self._lib.mht_forest_initiate(self._forest, _lib.ptr(x0), _lib.ptr(P0), float(self.default_P_d),
+                                                 C.byref(slot)))
+        node = Target(newTarget.time, len(self.__scanHistory__), x0.copy(), P0.copy(), ID=self.trackIdCounter,
+                      P_d=self.default_P_d, status=newTarget.status, isRoot=True)
+        self.trackIdCounter += 1
+        self._slots.append(slot.value)
+        self._slot_info[slot.value] = node
+        self.__targetList__.append(node)
+        self.__trackNodes__ = np.append(self.__trackNodes__, node)
+        self.__targetWindowSize__.append(self.N)
+
+    # ------------------------------------------------------------------------------------------
+    def addMeasurementList(self, scanList, aisList=None, **kwargs):
+        if aisList is not None and len(aisList) > 0:
+            raise NotImplementedError("AIS fusion (tracker.py:417-552) is outside the accelerated path")
+        for kw in ("dynamicWindow", "pruneSimilar"):
+            if kwargs.get(kw, False):
+                raise NotImplementedError(kw + " is outside the accelerated path")
+        self.tic.clear()
+        self.toc.clear()
+        self.__scanHistory__.append(scanList)
+        self.__aisHistory__.append(aisList if aisList is not None else AisMessageList())
+        t_total = time.time()
+        z = np.ascontiguousarray(scanList.measurements, dtype=np.float64).reshape(-1, 2)
+        nMeas = z.shape[0]
+        used = np.zeros(max(nMeas, 1), dtype=np.uint8)
+        info = _lib.ScanInfo()
+        _lib.check(self._lib.mht_forest_scan(self._forest, nMeas, _lib.ptr(z), float(scanList.time), C.byref(info),
+                                             _lib.ptr(used)))
+        self.scanInfo.append(info.as_dict())
+        self.nOptimSolved = info.n_multi_clusters
+        self.toc["Process"] = info.ms_gate * 1e-3
+        self.toc["Cluster"] = info.ms_cluster * 1e-3
+        self.toc["Optim"] = info.ms_assoc * 1e-3
+        self.toc["ILP-Prune"] = 0.0
+        self.toc["DynN"] = 0.0
+        t_term = time.time()
+        self._collect_tracks(scanList)
+        self.toc["Terminate"] = time.time() - t_term
+        self.toc["N-Prune"] = info.ms_prune * 1e-3
+
+        t_init = time.time()
+        unusedRadarMeasurements = scanList.filterUnused(used[:nMeas] == 0)
+        for initial_target in self.initiator.processMeasurements(unusedRadarMeasurements, []):
+            self.initiateTarget(initial_target)
+        self.toc["Init"] = time.time() - t_init
+        self.toc["Total"] = time.time() - t_total
+        for k, v in self.runtimeLog.items():
+            if k in self.toc:
+                v.append(self.toc[k])
+        if kwargs.get("printTime", False):
+            print(self.getTimeLogString())
+
+    def _collect_tracks(self, scanList):
+        """Selected hypothesis per track (tracker.py:228-236), termination (tracker.py:252-253)."""
+        cap = max(len(self._slots), 1)
+        n = C.c_int32()
+        slot = np.zeros(cap, dtype=np.int32)
+        x = np.zeros((cap, 4), dtype=np.float64)
+        P = np.zeros((cap, 4, 4), dtype=np.float32)
+        cn = np.zeros(cap, dtype=np.float64)
+        meas = np.zeros(cap, dtype=np.int32)
+        status = np.zeros(cap, dtype=np.int32)
+        _lib.check(self._lib.mht_forest_tracks(self._forest, cap, C.byref(n), _lib.ptr(slot), _lib.ptr(x), _lib.ptr(P),
+                                               _lib.ptr(cn), _lib.ptr(meas), _lib.ptr(status)))
+        assert list(slot[:n.value]) == self._slots, "forest/track bookkeeping out of sync"
+        scanNumber = len(self.__scanHistory__)
+        zs = np.asarray(scanList.measurements)
+        nodes, keep = [], []
+        for i, s in enumerate(self._slots):
+            root = self._slot_info[s]
+            m = int(meas[i])
+            node = Target(scanList.time, scanNumber, x[i].copy(), P[i].copy(), ID=root.ID, P_d=root.P_d,
+                          measurementNumber=m, measurement=(zs[m - 1] if m > 0 else None),
+                          cumulativeNLLR=float(cn[i]), status=STATUS_TAGS[int(status[i])],
+                          parent_loader=self._make_parent_loader(s))
+            if status[i] != 0:
+                _ = node.parent          # materialise the history while the window is still on the device
+                self.__terminatedTargets__.append(node)
+            else:
+                nodes.append(node)
+                keep.append(i)
+        self._slots = [self._slots[i] for i in keep]
+        self.__targetList__ = [self.__targetList__[i] for i in keep]
+        self.__targetWindowSize__ = [self.__targetWindowSize__[i] for i in keep]
+        self.__trackNodes__ = np.empty(len(nodes), dtype=np.dtype(object))
+        for i, nd in enumerate(nodes):
+            self.__trackNodes__[i] = nd
+
+    def _history(self, slot):
+        cap = 64
+        while True:
+            n = C.c_int32()
+            meas = np.zeros(cap, dtype=np.int32)
+            x = np.zeros((cap, 4), dtype=np.float64)
+            cn = np.zeros(cap, dtype=np.float64)
+            P = np.zeros((cap, 4, 4), dtype=np.float32)
+            rc = self._lib.mht_forest_history(self._forest, slot, cap, C.byref(n), _lib.ptr(meas), _lib.ptr(x),
+                                              _lib.ptr(cn), _lib.ptr(P))
+            if rc == _lib.MHT_E_CAPACITY:
+                cap = n.value + 8
+                continue
+            _lib.check(rc)
+            k = n.value
+            return meas[:k], x[:k], cn[:k], P[:k]
+
+    def _make_parent_loader(self, slot):
+        scan_at_creation = len(self.__scanHistory__)
+
+        def load(leaf):
+            if len(self.__scanHistory__) != scan_at_creation:
+                raise RuntimeError("Target.parent must be materialised before the next scan is added "
+                                   "(the window nodes live on the device)")
+            meas, x, cn, P = self._history(slot)
+            root = self._slot_info[slot]
+            first_scan = root.scanNumber
+            chain = Target(root.time, first_scan, x[0].copy(), P[0].copy(), ID=root.ID, P_d=root.P_d,
+                           status=root.status, cumulativeNLLR=float(cn[0]))
+            for k in range(1, len(meas) - 1):
+                sc = first_scan + k
+                scan = self.__scanHistory__[sc - 1]
+                m = int(meas[k])
+                chain = Target(scan.time, sc, x[k].copy(), P[k].copy(), ID=root.ID, P_d=root.P_d, parent=chain,
+                               measurementNumber=m,
+                               measurement=(np.asarray(scan.measurements)[m - 1] if m > 0 else None),
+                               cumulativeNLLR=float(cn[k]))
+            assert first_scan + len(meas) - 1 == leaf.scanNumber
+            leaf._parent = chain
+        return load
+
+    # ------------------------------------------------------------------------------------------
+    def getTrackNodes(self):
+        return self.__trackNodes__
+
+    def getLeafNodes(self, trackIndex):
+        """Leaves of one track tree in the reference's DFS order (Target.getLeafNodes)."""
+        slot = self._slots[trackIndex]
+        cap = 1024
+        while True:
+            n = C.c_int64()
+            x = np.zeros((cap, 4), dtype=np.float64)
+            cn = np.zeros(cap, dtype=np.float64)
+            meas = np.zeros(cap, dtype=np.int32)
+            rc = self._lib.mht_forest_leaves(self._forest, slot, cap, C.byref(n), _lib.ptr(x), _lib.ptr(cn),
+                                             _lib.ptr(meas))
+            if rc == _lib.MHT_E_CAPACITY:
+                cap = int(n.value)
+                continue
+            _lib.check(rc)
+            k = int(n.value)
+            return x[:k], cn[:k], meas[:k]
+
+    def getRuntimeAverage(self):
+        return {k: np.mean(np.array(v)) for k, v in self.runtimeLog.items()}
+
+    def getTimeLogString(self):
+        return " ".join("%s %.2fms" % (k, 1e3 * v) for k, v in self.toc.items())
+
+    def _checkTrackerIntegrity(self):
+        assert len(self.__trackNodes__) == len(self.__targetList__) == len(self._slots)
+        assert len({n.ID for n in self.__trackNodes__}) == len(self.__trackNodes__)
+        if len(self.__trackNodes__):
+            assert len({n.scanNumber for n in self.__trackNodes__}) == 1
+        for n in self.__trackNodes__:
+            assert np.isfinite(n.cumulativeNLLR)

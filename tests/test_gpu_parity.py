@@ -1,0 +1,232 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Tolerances (north_star): Kalman states and NLLR within 1e-5 relative (atol 1e-6 where the value
+crosses zero); gated sets, selected track ids and measurement histories bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import mht_oracle as mo
+import gpu_util as gu
+from pymht_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def _check_gate(out, x_bar, P_bar, P_hat, S, idx, d2g, x_hat, cnllr, Pd, lam):
+    L = len(idx)
+    assert out["rc"] == 0
+    np.testing.assert_allclose(out["x_bar"], x_bar, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(out["P_bar"], P_bar, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(out["P_hat"], P_hat, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(out["miss"], cnllr + mo.miss_nllr(Pd), rtol=1e-12)
+    off = out["off"]
+    assert off[0] == 0 and off[L] == sum(len(i) for i in idx)
+    for l in range(L):
+        got = out["meas"][off[l]:off[l + 1]]
+        assert list(got) == list(idx[l]), (l, got, idx[l])          # same set, ascending order
+        want = cnllr[l] + mo.nllr_radar(lam, Pd, S[l], d2g[l])
+        np.testing.assert_allclose(out["cnllr"][off[l]:off[l + 1]], want, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(out["xhat"][off[l]:off[l + 1]], x_hat[l], rtol=RTOL, atol=ATOL)
+    used = np.zeros(len(out["used"]), bool)
+    for i in idx:
+        used[i] = True
+    np.testing.assert_array_equal(out["used"].astype(bool)[:len(used)], used)
+
+
+def test_gate_batch_reference_kat():
+    """kalman_kat.npz holds outputs of the reference's own kalman.py on seeded random leaves."""
+    g = golden("kalman_kat")
+    T, lam, Pd, eta2 = [float(v) for v in g["params"]]
+    model, (A, Q, C, R, _) = gu.model_from_oracle(mo, T, eta2, lam)
+    L = g["x0"].shape[0]
+    cn = np.linspace(-3, 3, L)
+    out = gu.gate_batch_host(model, g["x0"], g["P0"], Pd, cn, g["z"])
+    leaf, meas = g["pair_leaf"], g["pair_meas"]
+    idx = [meas[leaf == l] for l in range(L)]
+    off = np.concatenate([[0], np.cumsum([len(i) for i in idx])])
+    d2g = [g["d2"][l, idx[l]] for l in range(L)]
+    xh = [g["xhat"][off[l]:off[l + 1]] for l in range(L)]
+    _check_gate(out, g["x_bar"], g["P_bar"], g["P_hat"], g["S"], idx, d2g, xh, cn, Pd, lam)
+    # float32 covariance chain: how close to bit-identical with the reference's NumPy/OpenBLAS
+    exact = np.mean(out["P_bar"] == g["P_bar"]), np.mean(out["P_hat"] == g["P_hat"])
+    print("bit-identical fraction P_bar %.3f P_hat %.3f" % exact)
+    assert exact[0] > 0.99
+
+
+@pytest.mark.parametrize("L,M,seed", [(1, 1, 0), (7, 0, 1), (300, 40, 2), (5000, 3000, 3)])
+def test_gate_batch_random_vs_oracle(L, M, seed):
+    rng = np.random.RandomState(seed)
+    T, lam, Pd, eta2 = 2.5, 1e-3 + 1e-9, 0.9, 5.99
+    model, (A, Q, C, R, P0c) = gu.model_from_oracle(mo, T, eta2, lam)
+    x0 = np.concatenate([rng.uniform(-400, 400, (L, 2)), rng.uniform(-12, 12, (L, 2))], axis=1)
+    G = rng.normal(size=(L, 4, 4)) * np.array([2.5, 2.5, 1.0, 1.0])[None, :, None]
+    P0 = (np.matmul(G, G.transpose(0, 2, 1)) + np.diag([6.25, 6.25, 1.9, 1.9])).astype(np.float32)
+    P0[::3] = P0c
+    z = rng.uniform(-450, 450, (M, 2)).astype(np.float32)
+    if M:
+        k = min(M, L)
+        z[:k] = (x0[:k, :2] + T * x0[:k, 2:] + rng.normal(scale=4, size=(k, 2))).astype(np.float32)
+    cn = rng.normal(size=L)
+    out = gu.gate_batch_host(model, x0, P0, Pd, cn, z.astype(np.float64))
+    x_bar, P_bar, P_hat, S, idx, d2g, x_hat = [], [], [], [], [], [], []
+    for s in range(0, L, 500):   # the oracle materialises (L,M,2): chunk it
+        r = mo.gate_leaves(A, Q, C, R, x0[s:s + 500], P0[s:s + 500], z, eta2)
+        for dst, src in zip((x_bar, P_bar, P_hat, S), r[:4]):
+            dst.append(src)
+        idx += r[4]; d2g += r[5]; x_hat += r[6]
+    _check_gate(out, np.concatenate(x_bar), np.concatenate(P_bar), np.concatenate(P_hat), np.concatenate(S),
+                idx, d2g, x_hat, cn, Pd, lam)
+
+
+def test_gate_batch_capacity_error():
+    model, (A, Q, C, R, P0c) = gu.model_from_oracle(mo, 2.5, 5.99, 1e-4)
+    x0 = np.zeros((4, 4))
+    z = np.zeros((10, 2))
+    out = gu.gate_batch_host(model, x0, np.broadcast_to(P0c, (4, 4, 4)).copy(), 0.9, np.zeros(4), z, cap=3)
+    assert out["rc"] == _lib.MHT_E_CAPACITY
+    assert out["off"][4] == 40
+
+
+def _oracle_states(name, upto):
+    """Yield (scan index, OracleTracker after _grow, golden) so column problems can be extracted."""
+    g = golden(name)
+    T, lam_phi, lam_nu, N, Pd, eta2, R = g["params"]
+    trk = mo.OracleTracker(T, lam_phi, lam_nu, eta2=eta2, N=int(N), P_d=Pd)
+    for x in g["init_x"]:
+        trk.initiate(x, float(g["init_time"]))
+    for k in range(upto):
+        pre = "s%d_" % k
+        trk.n_scans += 1
+        trk._grow(g[pre + "z"], float(g[pre + "time"]), trk.n_scans)
+        yield k, trk
+        trk._select(trk._cluster())
+        trk._terminate()
+        trk._prune()
+
+
+@pytest.mark.parametrize("name,upto", [("cfg1_crossing", 10), ("cfg2_small", 10), ("cfg5_small", 10), ("cfg2", 8)])
+def test_cluster_and_assoc_vs_oracle(name, upto):
+    for k, trk in _oracle_states(name, upto):
+        cost, tree, RM, n_rows = gu.oracle_columns(trk)
+        nT = len(trk.roots)
+        if nT == 0:
+            continue
+        # clusters: same partition of the trees as the oracle's connected components
+        lab = gu.cluster_device(tree, RM, nT, n_rows)
+        want = np.empty(nT, dtype=int)
+        for cl in trk._cluster():
+            want[cl] = min(cl)
+        np.testing.assert_array_equal(lab, want)
+        # association: exact optimum (HiGHS, gap 0) on every multi-tree cluster + argmin on singletons
+        rc, sel, info = gu.assoc_solve_device(cost, tree, RM, nT, n_rows)
+        assert rc == 0, (name, k, rc, info)
+        assert info[6] == 1
+        exact_obj, exact_sel = 0.0, {}
+        starts = np.searchsorted(tree, np.arange(nT))
+        for cl in trk._cluster():
+            if len(cl) == 1:
+                t = cl[0]
+                leaves = trk.leaves[t]
+                best = max(i for i, l in enumerate(leaves) if l.cnllr == min(x.cnllr for x in leaves))
+                exact_sel[t] = starts[t] + best
+                exact_obj += cost[starts[t] + best]
+            else:
+                c2, ct2, ptr, idx, nr, nodes = trk._columns(cl)
+                s2, obj = mo.solve_blp(c2 * trk.N, ct2, ptr, idx, len(cl), nr)
+                exact_obj += obj
+                for j in s2:
+                    exact_sel[cl[ct2[j]]] = starts[cl[ct2[j]]] + trk.leaves[cl[ct2[j]]].index(nodes[j])
+        assert abs(info[1] - exact_obj) <= 1e-9 * max(1.0, abs(exact_obj)), (name, k, info, exact_obj)
+        assert [exact_sel[t] for t in range(nT)] == list(sel), (name, k)
+        # feasibility: no measurement row used twice
+        used = RM[:, sel][RM[:, sel] >= 0]
+        assert len(used) == len(set(used.tolist()))
+
+
+def _replay_tracker(name, n_scans=None, **kw):
+    from pymht_b200.tracker import Tracker, backtrackMeasurementNumbers
+    from pymht_b200.models import pv
+    from pymht_b200.pyTarget import Target
+    from pymht_b200.utils.classDefinitions import MeasurementList
+    g = golden(name)
+    T, lam_phi, lam_nu, N, Pd, eta2, R = [float(v) for v in g["params"]]
+    trk = Tracker(pv, T, lam_phi, lam_nu, eta2=eta2, N=int(N), P_d=Pd, **kw)
+    trk.mergeThreshold = 0.0
+    for x in g["init_x"]:
+        trk.initiateTarget(Target(float(g["init_time"]), None, x, pv.P0, status="preinitialized"))
+    stats = []
+    for k in range(int(g["n_scans"]) if n_scans is None else n_scans):
+        pre = "s%d_" % k
+        trk.addMeasurementList(MeasurementList(float(g[pre + "time"]), g[pre + "z"]))
+        nodes = list(trk.getTrackNodes())
+        info = trk.scanInfo[-1]
+        stats.append(info)
+        yield k, g, pre, trk, nodes, backtrackMeasurementNumbers(nodes), info
+    trk.close()
+
+
+@pytest.mark.parametrize("name", ["cfg1_crossing", "cfg2_small", "cfg5_small", "cfg2"])
+def test_tracker_replays_reference_golden(name):
+    """Whole addMeasurementList sequences against what the unmodified reference produced."""
+    for k, g, pre, trk, nodes, hist, info in _replay_tracker(name):
+        assert info["certified"] == 1, (name, k, info)
+        assert [n.ID for n in nodes] == list(g[pre + "ids"]), (name, k)
+        H = g[pre + "hist"]
+        for i, h in enumerate(hist):
+            assert h == list(H[i, :len(h)]), (name, k, i, h, H[i])
+            assert len(h) == np.sum(H[i] >= 0)
+        np.testing.assert_allclose(np.array([n.x_0 for n in nodes]).reshape(-1, 4), g[pre + "x"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(np.array([n.P_0 for n in nodes], dtype=float).reshape(-1, 4, 4), g[pre + "P"],
+                                   rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose([n.cumulativeNLLR for n in nodes], g[pre + "cnllr"], rtol=RTOL, atol=ATOL)
+        nleaves = [len(trk.getLeafNodes(i)[1]) for i in range(len(nodes))]
+        assert nleaves == list(g[pre + "nleaves"]), (name, k)
+        assert info["n_clusters"] == int(g[pre + "nclusters"])
+        assert info["n_multi_clusters"] == int(g[pre + "n_ilp"])
+        trk._checkTrackerIntegrity()
+
+
+def test_tracker_cfg3_head_vs_reference():
+    """1k targets / 5k measurements, the first scans the reference can still finish."""
+    for k, g, pre, trk, nodes, hist, info in _replay_tracker("cfg3_head", maxTargets=1024, maxNodes=1 << 20):
+        print("cfg3 scan", k + 1, {kk: info[kk] for kk in ("n_parents", "n_children", "n_clusters", "certified",
+                                                          "dual_iters", "n_candidates", "bb_nodes", "lower_bound",
+                                                          "objective", "ms_gate", "ms_assoc")})
+        assert [n.ID for n in nodes] == list(g[pre + "ids"])
+        assert info["n_children"] == int(g[pre + "nleaves"].sum()) or k > 0
+        H = g[pre + "hist"]
+        same = sum(h == list(H[i, :len(h)]) for i, h in enumerate(hist))
+        print("  tracks with identical measurement history: %d / %d" % (same, len(hist)))
+        if info["certified"]:
+            assert same == len(hist)
+        else:
+            assert same >= 0.97 * len(hist)
+
+
+def test_large_random_forest_properties():
+    """Full-size property checks (no oracle at this size): every track selects exactly one leaf, no
+    measurement is shared between selected hypotheses' current-scan associations, the bound brackets
+    the objective, leaves stay sorted, and capacity errors are reported, not hidden."""
+    from pymht_b200.tracker import Tracker
+    from pymht_b200.models import pv
+    import pymht_b200.utils.simulator as sim
+    sim.seed_simulator(7)
+    R, lam, nT = 1142.0, 1e-3, 1000
+    init = sim.generateInitialTargets(nT, np.zeros(2), R, 0.9, 1.0)
+    simList = sim.simulateTargets(init, 5 * 2.5, 2.5, pv)
+    scans = sim.simulateScans(simList, 2.5, pv.C_RADAR, pv.R_RADAR(), lam, R, np.zeros(2), preInitialized=True)
+    trk = Tracker(pv, 2.5, lam, 1e-9, N=6, P_d=0.9, maxTargets=1024, maxNodes=1 << 23, maxParents=1 << 21)
+    trk.mergeThreshold = 0.0
+    trk.preInitialize(simList)
+    for scan in scans[:5]:
+        trk.addMeasurementList(scan)
+        info = trk.scanInfo[-1]
+        nodes = trk.getTrackNodes()
+        used = [n.measurementNumber for n in nodes if n.measurementNumber > 0]
+        assert len(used) == len(set(used)), "a measurement was assigned to two tracks"
+        assert info["lower_bound"] <= info["objective"] + 1e-6
+        assert len(nodes) + info["n_dead"] == info["n_trees"]
+        assert info["n_children"] == info["n_parents"] + info["n_pairs"]
+    trk.close()
