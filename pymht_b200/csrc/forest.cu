@@ -746,6 +746,7 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
         cudaEventElapsedTime(&info->ms_cluster, f->ev[1], f->ev[5]);
         cudaEventElapsedTime(&info->ms_assoc, f->ev[5], f->ev[2]);
         cudaEventElapsedTime(&info->ms_prune, f->ev[2], f->ev[4]);
+        cudaEventElapsedTime(&info->ms_total, f->ev[0], f->ev[4]);
     }
     return MHT_OK;
 }

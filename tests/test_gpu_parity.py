@@ -12,14 +12,23 @@ from pymht_b200 import _lib
 
 pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-5, 1e-6
+XATOL = 1e-5   # states: 1e-5 relative, floor 1e-5 m (m/s) where a coordinate crosses zero (sigma_R is 2.5 m)
+
+
+def assert_cov_close(got, want):
+    """float32 covariances: 1e-5 relative to each matrix's scale.  P_hat = P_bar - K C P_bar cancels,
+    so single elements differ from the reference's LAPACK-inverse chain by ~1 ulp OF THE OPERANDS."""
+    got, want = np.asarray(got, dtype=float), np.asarray(want, dtype=float)
+    scale = np.abs(want).reshape(want.shape[0], -1).max(axis=1)[:, None, None]
+    assert np.all(np.abs(got - want) <= RTOL * scale), float(np.max(np.abs(got - want) / scale))
 
 
 def _check_gate(out, x_bar, P_bar, P_hat, S, idx, d2g, x_hat, cnllr, Pd, lam):
     L = len(idx)
     assert out["rc"] == 0
     np.testing.assert_allclose(out["x_bar"], x_bar, rtol=1e-12, atol=1e-9)
-    np.testing.assert_allclose(out["P_bar"], P_bar, rtol=RTOL, atol=ATOL)
-    np.testing.assert_allclose(out["P_hat"], P_hat, rtol=RTOL, atol=ATOL)
+    assert_cov_close(out["P_bar"], P_bar)
+    assert_cov_close(out["P_hat"], P_hat)
     np.testing.assert_allclose(out["miss"], cnllr + mo.miss_nllr(Pd), rtol=1e-12)
     off = out["off"]
     assert off[0] == 0 and off[L] == sum(len(i) for i in idx)
@@ -28,7 +37,7 @@ def _check_gate(out, x_bar, P_bar, P_hat, S, idx, d2g, x_hat, cnllr, Pd, lam):
         assert list(got) == list(idx[l]), (l, got, idx[l])          # same set, ascending order
         want = cnllr[l] + mo.nllr_radar(lam, Pd, S[l], d2g[l])
         np.testing.assert_allclose(out["cnllr"][off[l]:off[l + 1]], want, rtol=RTOL, atol=ATOL)
-        np.testing.assert_allclose(out["xhat"][off[l]:off[l + 1]], x_hat[l], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(out["xhat"][off[l]:off[l + 1]], x_hat[l], rtol=RTOL, atol=XATOL)
     used = np.zeros(len(out["used"]), bool)
     for i in idx:
         used[i] = True
@@ -177,9 +186,9 @@ def test_tracker_replays_reference_golden(name):
         for i, h in enumerate(hist):
             assert h == list(H[i, :len(h)]), (name, k, i, h, H[i])
             assert len(h) == np.sum(H[i] >= 0)
-        np.testing.assert_allclose(np.array([n.x_0 for n in nodes]).reshape(-1, 4), g[pre + "x"], rtol=RTOL, atol=ATOL)
-        np.testing.assert_allclose(np.array([n.P_0 for n in nodes], dtype=float).reshape(-1, 4, 4), g[pre + "P"],
-                                   rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(np.array([n.x_0 for n in nodes]).reshape(-1, 4), g[pre + "x"], rtol=RTOL, atol=XATOL)
+        if nodes:
+            assert_cov_close(np.array([n.P_0 for n in nodes]).reshape(-1, 4, 4), g[pre + "P"])
         np.testing.assert_allclose([n.cumulativeNLLR for n in nodes], g[pre + "cnllr"], rtol=RTOL, atol=ATOL)
         nleaves = [len(trk.getLeafNodes(i)[1]) for i in range(len(nodes))]
         assert nleaves == list(g[pre + "nleaves"]), (name, k)
