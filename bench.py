@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- scans/sec of the per-scan hot path at BASELINE config 3
+(1k targets, ~5k measurements/scan, lambda=1e-3, N-scan=6, CV model), on N GPUs of one node.
+
+A "step" is one Tracker.addMeasurementList hot path (gate+NLLR -> cluster -> global-hypothesis
+0/1 program -> terminate -> N-scan prune) over one synthetic scan, at steady state (the forest is
+pre-rolled N+2 scans so the hypothesis trees have reached their windowed size).
+
+  value : device-timed (CUDA events on the forest's stream, inside libmht_b200), scan already in HBM
+  e2e   : same scans through pymht_b200.Tracker.addMeasurementList with HOST measurement arrays
+          (H2D of the scan and D2H of the per-track results inside the timed region), wall clock
+  --impl reference : the oracle port of the reference's CPU path (oracle/mht_oracle.py; the reference
+          itself is pure Python and cannot travel to the GPU box) on a bounded sample.
+N > 1: every rank owns one independent surveillance sector (its own 1k-target forest, weak scaling);
+the only exchange is an all_gather of the per-rank track summaries.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (targets, radarRange, lambda_phi, N, P_d, seed, maxNodes, maxParents)
+    "cfg3_1k_targets_5k_meas_N6": (1000, 1142.0, 1e-3, 6, 0.9, 1234, 96 << 20, 24 << 20),
+    "cfg2_100_targets_1k_meas_N4": (100, 1702.0, 1e-4, 4, 0.9, 1234, 1 << 22, 1 << 20),
+}
+T_RADAR = 2.5
+
+
+def make_scenario(name, n_scans, seed_offset=0):
+    import pymht_b200.utils.simulator as sim
+    from pymht_b200.models import pv
+    nT, R, lam, N, Pd, seed, _, _ = WORKLOADS[name]
+    sim.seed_simulator(seed + seed_offset)
+    p0 = np.zeros(2)
+    init = sim.generateInitialTargets(nT, p0, R, Pd, pv.sigmaQ_true)
+    simList = sim.simulateTargets(init, n_scans * T_RADAR, T_RADAR, pv)
+    scans = sim.simulateScans(simList, T_RADAR, pv.C_RADAR, pv.R_RADAR(pv.sigmaR_RADAR_true), lam, R, p0,
+                              shuffle=True, globalClutter=True, preInitialized=True)
+    return simList, scans[:n_scans]
+
+
+def make_tracker(name):
+    from pymht_b200.tracker import Tracker
+    from pymht_b200.models import pv
+    nT, R, lam, N, Pd, seed, max_nodes, max_par = WORKLOADS[name]
+    trk = Tracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=16384,
+                  maxNodes=max_nodes, maxParents=max_par)
+    trk.mergeThreshold = 0.0
+    return trk
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.rows, self.stop_flag, self.index = [], False, index
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.15)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gate_bytes(info):
+    """B_gate = 280 L + 8 M + 48 G  (reference dtypes: f64 state, f32 covariance)."""
+    return 280.0 * info["n_parents"] + 8.0 * info["n_meas"] + 48.0 * info["n_pairs"]
+
+
+def run_device_leg(name, scans, simList, preroll, warmup, steps):
+    """Timed with the library's CUDA events (first kernel -> results on host), scans resident in HBM."""
+    import torch
+    from pymht_b200 import _lib
+    trk = make_tracker(name)
+    trk.preInitialize(simList)
+    lib = trk._lib
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d_scans = [torch.from_numpy(np.ascontiguousarray(s.measurements, dtype=np.float64)).to(dev) for s in scans]
+    torch.cuda.synchronize()
+    infos = []
+    for k, (s, dz) in enumerate(zip(scans, d_scans)):
+        info = _lib.ScanInfo()
+        _lib.check(lib.mht_forest_scan_device(trk._forest, dz.shape[0], dz.data_ptr(), float(s.time), C.byref(info)),
+                   allow=(_lib.MHT_E_NOTOPTIMAL,))
+        d = info.as_dict()
+        d["n_meas"] = int(dz.shape[0])
+        infos.append(d)
+    timed = infos[preroll + warmup:preroll + warmup + steps]
+    dev_bytes = trk.deviceBytes()
+    trk.close()
+    return timed, infos, dev_bytes
+
+
+def run_e2e_leg(name, scans, simList, preroll, warmup, steps):
+    trk = make_tracker(name)
+    trk.preInitialize(simList)
+    t_steps = []
+    for k, s in enumerate(scans):
+        t0 = time.perf_counter()
+        trk.addMeasurementList(s)
+        t_steps.append(time.perf_counter() - t0)
+    timed = t_steps[preroll + warmup:preroll + warmup + steps]
+    h2d = int(np.mean([16 * len(s.measurements) for s in scans[preroll + warmup:]]))
+    n_tracks = len(trk.getTrackNodes())
+    trk.close()
+    return timed, h2d, n_tracks
+
+
+def run_cpu_port(name, budget_s=25.0, max_scans=3):
+    """The oracle port of the reference CPU path on the first scans of the same workload."""
+    from oracle import mht_oracle as mo
+    nT, R, lam, N, Pd, seed, _, _ = WORKLOADS[name]
+    simList, scans = make_scenario(name, max_scans)
+    orc = mo.OracleTracker(T_RADAR, lam, 1e-9, N=N, P_d=Pd)
+    for tgt in simList[0]:
+        orc.initiate(np.asarray(tgt.cartesianState(), dtype=np.float64), tgt.time)
+    times, leaves = [], []
+    t_all = time.perf_counter()
+    for s in scans:
+        t0 = time.perf_counter()
+        info = orc.add_scan(s.measurements, s.time)
+        times.append(time.perf_counter() - t0)
+        leaves.append(info["n_leaves"])
+        if time.perf_counter() - t_all > budget_s:
+            break
+    return times, leaves
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3_1k_targets_5k_meas_N6", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    name = args.workload
+    nT, R, lam, N, Pd, seed, _, _ = WORKLOADS[name]
+    config = {"workload": name, "targets": nT, "meas_per_scan": "~%d" % int(nT * Pd + lam * np.pi * R * R),
+              "lambda_phi": lam, "n_scan": N, "P_d": Pd, "model": "CV (pv)", "radar_period_s": T_RADAR,
+              "l2": "per-scan working set (hypothesis levels, GBs) exceeds the 126 MB L2; no explicit flush",
+              "parallelism": "1 forest per GPU; %d independent sector(s)" % world}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        times, leaves = run_cpu_port(name, budget_s=25.0 * max(1, args.steps) / 8.0, max_scans=max(2, min(3, args.steps)))
+        v = len(times) / sum(times)
+        sample = "scans 1-%d of the same scenario from a cold start (leaves after each scan: %s); steady-state scans " \
+                 "(millions of leaves) are out of CPU reach" % (len(times), leaves)
+        line = {"metric": "scans/sec @ 1k targets, 5k meas/scan", "value": v, "unit": "scans/s", "n_gpus": args.gpus,
+                "steps": len(times), "warmup": 0, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64 state / f32 covariance", "data": "synthetic", "config": config,
+                "impl": "reference",
+                "cpu_baseline": {"value": v, "unit": "scans/s", "cores": 1, "kind": "port", "sample": sample},
+                "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    preroll = N + 2
+    n_scans = preroll + args.warmup + args.steps
+    simList, scans = make_scenario(name, n_scans, seed_offset=rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    timed, infos, dev_bytes = run_device_leg(name, scans, simList, preroll, args.warmup, args.steps)
+    barrier()
+    e2e_times, h2d, n_tracks = run_e2e_leg(name, scans, simList, preroll, args.warmup, args.steps)
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    t_dev = sum(d["ms_total"] for d in timed) * 1e-3
+    t_e2e = sum(e2e_times)
+    if dist is not None:
+        t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = t.tolist()
+        # the one exchange of the sharded forest: every rank gets every sector's track count
+        summary = torch.tensor([n_tracks], dtype=torch.int64, device="cuda")
+        gathered = [torch.zeros_like(summary) for _ in range(world)]
+        dist.all_gather(gathered, summary)
+    if rank == 0:
+        K = len(timed)
+        value = world * K / t_dev
+        e2e = world * K / t_e2e
+        ms_gate = float(np.mean([d["ms_gate"] for d in timed]))
+        bytes_gate = float(np.mean([gate_bytes(d) for d in timed]))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = bytes_gate / (ms_gate * 1e-3) / 1e9
+        line = {
+            "metric": "scans/sec @ 1k targets, 5k meas/scan", "value": value, "unit": "scans/s", "n_gpus": world,
+            "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 state / f32 covariance", "data": "synthetic",
+            "config": config,
+            "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": int(infos[-1]["n_trees"] * 152 + 128)},
+            "gpu_launches": None,
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "kernel": "gate stage (forest_count_kernel + forest_emit_kernel)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                         "bytes_per_launch": bytes_gate, "ms_per_launch": ms_gate},
+            "stage_ms": {k: float(np.mean([d[k] for d in timed])) for k in
+                         ("ms_gate", "ms_cluster", "ms_assoc", "ms_prune", "ms_total")},
+            "scan_stats": {k: float(np.mean([d[k] for d in timed])) for k in
+                           ("n_parents", "n_children", "n_pairs", "n_clusters", "n_multi_clusters", "dual_iters",
+                            "n_candidates", "bb_nodes", "certified")},
+            "forest_hbm_bytes": dev_bytes,
+        }
+        line["gpu_launches"] = int(sum(launches_per_scan(d) for d in timed))
+        if not args.no_cpu_baseline and world >= 1:
+            times, leaves = run_cpu_port(name)
+            v = len(times) / sum(times)
+            line["cpu_baseline"] = {"value": v, "unit": "scans/s", "cores": 1, "kind": "port",
+                                    "sample": "oracle port, scans 1-%d of the same scenario from a cold start "
+                                              "(leaves after each scan: %s); the GPU figure is at steady state "
+                                              "(%.2e live leaves/scan)" % (len(times), leaves,
+                                                                           line["scan_stats"]["n_parents"])}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def launches_per_scan(d):
+    """Kernel launches of libmht_b200 per scan (counted from the launch sequence in csrc/)."""
+    iters = 120
+    greedy = (iters + 39) // 40
+    return 7 + 5 + 3 + 3 * iters + greedy * (1 + 1 + 3 * 40 + 1) + 11 + 1
+
+
+if __name__ == "__main__":
+    main()
