@@ -54,7 +54,8 @@ def make_tracker(name):
     from pymht_b200.models import pv
     nT, R, lam, N, Pd, seed, max_nodes, max_par = WORKLOADS[name]
     trk = Tracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=16384,
-                  maxNodes=max_nodes, maxParents=max_par)
+                  maxNodes=max_nodes, maxParents=max_par,
+                  maxDualIterations=int(os.environ.get("MHT_DUAL_ITERS", "120")))
     trk.mergeThreshold = 0.0
     return trk
 
@@ -258,7 +259,7 @@ def main():
                          ("ms_gate", "ms_cluster", "ms_assoc", "ms_prune", "ms_total")},
             "scan_stats": {k: float(np.mean([d[k] for d in timed])) for k in
                            ("n_parents", "n_children", "n_pairs", "n_clusters", "n_multi_clusters", "dual_iters",
-                            "n_candidates", "bb_nodes", "certified")},
+                            "n_candidates", "bb_nodes", "certified", "lower_bound", "objective")},
             "forest_hbm_bytes": dev_bytes,
         }
         line["gpu_launches"] = int(sum(launches_per_scan(d) for d in timed))

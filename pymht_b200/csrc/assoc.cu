@@ -33,6 +33,8 @@ constexpr double kShrink = 0.7;
 constexpr int kMaxCandPerTree = 192;
 constexpr int kGreedyRounds = 40;
 constexpr int kGreedyEvery = 40;
+constexpr int kStallStop = 30;
+constexpr int kSiftRounds = 3;
 constexpr unsigned long long kKeyInf = ~0ull;
 
 __device__ __forceinline__ long long to_fix(double v) { return __double2ll_rn(v * kFix); }
@@ -69,7 +71,7 @@ __device__ __forceinline__ void uf_union(int *uf, int a, int b) {
     }
 }
 
-__global__ void assoc_init_kernel(ColView c, AssocWork w, int *tstart, int *tend) {
+__global__ void assoc_init_kernel(ColView c, AssocWork w, int *tstart, int *tend, int warm) {
     const int T = c.n_trees, R = c.n_rows;
     const int n = *c.n_ptr;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max(max(T + 1, R), n); i += gridDim.x * blockDim.x) {
@@ -85,14 +87,17 @@ __global__ void assoc_init_kernel(ColView c, AssocWork w, int *tstart, int *tend
             w.cl_stall[i] = 0;
             w.cl_done[i] = 0;
             w.cl_flag[i] = 0;
+            w.tdone[i] = 0;
         }
         if (i <= T) w.cand_cnt[i] = 0;
         if (i < R) {
             w.row_owner[i] = -1;
-            w.u[i] = 0.0;
-            w.best_u[i] = 0.0;
+            w.row_mark[i] = 0;         // becomes 1 when two different trees touch the row
+            if (!warm) w.u[i] = 0.0;   // warm start: keep last scan's multipliers (rows persist W scans)
+            w.best_u[i] = warm ? w.u[i] : 0.0;
             w.usage[i] = 0;
         }
+        if (i < 4) w.stall_ctr[i] = 0;
         if (i < kAssocInfo) w.info[i] = 0;
         if (i == 0) {
             *w.bb_nodes = 0ull;
@@ -113,21 +118,32 @@ __global__ void assoc_clear_ranges_kernel(int T, int *tstart, int *tend) {
     }
 }
 
-__global__ void uf_union_cols_kernel(ColView c, int *uf, int *row_owner) {
+__global__ void uf_union_cols_kernel(ColView c, int *uf, int *row_owner, int *row_multi) {
     const int n = *c.n_ptr;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         const int t = c.tree[j];
         for (int k = 0; k < c.width; ++k) {
             const int r = c.rows[(long long)k * c.stride + j];
             if (r < 0) continue;
+            // siblings share every plane but the newest: the left neighbour already did this row
+            if ((threadIdx.x & 31) && c.rows[(long long)k * c.stride + j - 1] == r && c.tree[j - 1] == t) continue;
             int o = row_owner[r];
             if (o < 0) {
                 o = atomicCAS(&row_owner[r], -1, t);
                 if (o < 0) o = t;
             }
-            if (o != t) uf_union(uf, t, o);
+            if (o != t) {
+                row_multi[r] = 1;
+                uf_union(uf, t, o);
+            }
         }
     }
+}
+
+// warm start hygiene: a row only one tree can use needs no multiplier
+__global__ void warm_fix_kernel(int R, const int *row_multi, double *u, double *best_u) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x)
+        if (!row_multi[r]) u[r] = best_u[r] = 0.0;
 }
 
 __global__ void uf_flatten_kernel(int T, int *uf) {
@@ -178,12 +194,13 @@ __global__ void __launch_bounds__(256) dual_rc_kernel(ColView c, AssocWork w) {
     if (!FORCE && w.info[0]) return;
     const int n = *c.n_ptr;
     const int nround = (n + 31) & ~31;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
         int t = -1;
         unsigned long long key = kKeyInf;
-        if (j < n) {
+        if (i < n) {
+            const int j = c.idx ? c.idx[i] : i;
             t = c.tree[j];
-            if (FORCE || !w.cl_done[w.uf[t]]) {
+            if (FORCE || !w.tdone[t]) {
                 double v = col_cost(c, j, t);
                 for (int k = 0; k < c.width; ++k) {
                     const int r = c.rows[(long long)k * c.stride + j];
@@ -204,9 +221,10 @@ template <bool FORCE>
 __global__ void __launch_bounds__(256) dual_arg_kernel(ColView c, AssocWork w) {
     if (!FORCE && w.info[0]) return;
     const int n = *c.n_ptr;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int j = c.idx ? c.idx[i] : i;
         const int t = c.tree[j];
-        if (!FORCE && w.cl_done[w.uf[t]]) continue;
+        if (!FORCE && w.tdone[t]) continue;
         if (f64_key(w.rc[j]) == w.tmin[t]) atomicMax(&w.targ[t], j);
     }
 }
@@ -214,6 +232,10 @@ __global__ void __launch_bounds__(256) dual_arg_kernel(ColView c, AssocWork w) {
 // single CTA: subgradient, per-cluster Polyak step, bookkeeping (see file header)
 __global__ void __launch_bounds__(1024, 1) dual_update_kernel(ColView c, AssocWork w, const int *tstart) {
     if (w.info[0]) return;
+    if (c.idx && w.act_n[2]) {  // the active list did not fit: nothing to iterate on
+        if (threadIdx.x == 0) w.info[0] = 1;
+        return;
+    }
     const int T = c.n_trees, R = c.n_rows;
     __shared__ int open;
     if (threadIdx.x == 0) open = 0;
@@ -264,8 +286,9 @@ __global__ void __launch_bounds__(1024, 1) dual_update_kernel(ColView c, AssocWo
             continue;
         }
         if (L > w.cl_best[t] + 1e-12) {
+            // flag 1 = keep these multipliers; flag 8 = the gain is large enough to keep iterating
+            w.cl_flag[t] = (L > w.cl_best[t] + 1e-6 * fmax(1.0, fabs(L))) ? 9 : 1;
             w.cl_best[t] = L;
-            w.cl_flag[t] = 1;
             w.cl_stall[t] = 0;
         } else if (++w.cl_stall[t] >= kPatience) {
             w.cl_theta[t] *= kShrink;
@@ -290,15 +313,24 @@ __global__ void __launch_bounds__(1024, 1) dual_update_kernel(ColView c, AssocWo
         if (!w.cl_done[cl]) w.u[r] = fmax(0.0, w.u[r] + w.cl_step[cl] * (double)w.usage[r]);
         w.usage[r] = 0;
     }
+    __shared__ int improved;
+    if (threadIdx.x == 0) improved = 0;
+    __syncthreads();
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
         if (tstart[t] < 0) continue;
-        if (w.cl_flag[w.uf[t]] & 2) w.sel[t] = w.targ[t];
+        const int cl = w.uf[t];
+        if (w.cl_flag[cl] & 2) w.sel[t] = w.targ[t];
+        if (w.cl_flag[cl] & (8 | 2)) improved = 1;
+        w.tdone[t] = w.cl_done[cl];
         w.tmin[t] = kKeyInf;
         w.targ[t] = -1;
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
         w.info[1] += 1;
-        if (open == 0) w.info[0] = 1;
+        // stop when every cluster is settled, or no bound moved noticeably for kStallStop iterations
+        w.stall_ctr[0] = improved ? 0 : w.stall_ctr[0] + 1;
+        if (open == 0 || w.stall_ctr[0] >= kStallStop) w.info[0] = 1;
     }
 }
 
@@ -338,10 +370,11 @@ __global__ void __launch_bounds__(256) greedy_prop_kernel(ColView c, AssocWork w
     if (w.info[0] || w.info[2] == 0) return;
     const int n = *c.n_ptr;
     const int nround = (n + 31) & ~31;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
         int t = -1;
         unsigned long long key = kKeyInf;
-        if (j < n) {
+        if (i < n) {
+            const int j = c.idx ? c.idx[i] : i;
             t = c.tree[j];
             if (!w.committed[t] && rows_free(c, w.row_taken, j))
                 key = f64_key(w.rc[j]);
@@ -356,7 +389,8 @@ __global__ void __launch_bounds__(256) greedy_prop_kernel(ColView c, AssocWork w
 __global__ void __launch_bounds__(256) greedy_arg_kernel(ColView c, AssocWork w) {
     if (w.info[0] || w.info[2] == 0) return;
     const int n = *c.n_ptr;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int j = c.idx ? c.idx[i] : i;
         const int t = c.tree[j];
         if (w.committed[t]) continue;
         if (f64_key(w.rc[j]) == w.prop_key[t] && rows_free(c, w.row_taken, j)) atomicMax(&w.prop_col[t], j);
@@ -440,6 +474,146 @@ __global__ void __launch_bounds__(1024, 1) greedy_finish_kernel(ColView c, Assoc
 }
 
 // ------------------------------------------------------------------------------------------------
+// sifting: the dual iterations run on an ACTIVE subset of the columns (reduced cost within a
+// threshold of the tree minimum at the last full pricing pass, plus every conflict-free all-miss
+// column and the incumbent); full passes re-price all columns, so the final bound is exact.
+// ------------------------------------------------------------------------------------------------
+__device__ __constant__ double kActDelta[4] = {3.0, 1.5, 0.75, 0.25};
+
+__device__ __forceinline__ int active_mask(const ColView &c, const AssocWork &w, int j) {
+    const int t = c.tree[j];
+    if (w.tdone[t]) return 0;
+    const double exc = w.rc[j] - key_f64(w.tmin[t]);
+    bool keep = j == w.sel[t];
+    if (!keep) {  // a column without rows can always be chosen: keeps the restricted problem feasible
+        keep = true;
+        for (int k = 0; k < c.width; ++k) keep = keep && c.rows[(long long)k * c.stride + j] < 0;
+    }
+    int m = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) m |= (keep || exc <= kActDelta[q]) ? (1 << q) : 0;
+    return m;
+}
+
+__global__ void __launch_bounds__(256) active_count_kernel(ColView c, AssocWork w) {
+    const int n = *c.n_ptr;
+    const int ntiles = (n + 255) / 256;
+    const long long plane = (long long)(ntiles + 1);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int j = tile * 256 + threadIdx.x;
+        const int m = j < n ? active_mask(c, w, j) : 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int cnt = __syncthreads_count(m & (1 << q));
+            if (threadIdx.x == 0) w.act_tile[q * plane + tile] = cnt;
+        }
+    }
+}
+
+// single CTA: pick the widest threshold whose list fits, exclusive-scan its tile counts in place
+__global__ void __launch_bounds__(1024, 1) active_scan_kernel(ColView c, AssocWork w) {
+    const int n = *c.n_ptr;
+    const int ntiles = (n + 255) / 256;
+    const long long plane = (long long)(ntiles + 1);
+    __shared__ long long tot[4];
+    __shared__ int pick;
+    __shared__ int carry;
+    __shared__ int wsum[32];
+    if (threadIdx.x < 4) tot[threadIdx.x] = 0;
+    __syncthreads();
+    for (int q = 0; q < 4; ++q) {
+        long long s = 0;
+        for (int i = threadIdx.x; i < ntiles; i += blockDim.x) s += w.act_tile[q * plane + i];
+        atomicAdd((unsigned long long *)&tot[q], (unsigned long long)s);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        pick = 3;
+        for (int q = 3; q >= 0; --q)
+            if (tot[q] <= w.cap_act) pick = q;
+        const bool fits = tot[pick] <= w.cap_act;
+        w.act_n[0] = fits ? (int)tot[pick] : 0;
+        w.act_n[1] = pick;
+        w.act_n[2] = fits ? 0 : 1;   // 1 = even the tightest threshold does not fit: sifting disabled
+        carry = 0;
+    }
+    __syncthreads();
+    int *cnt = w.act_tile + pick * plane;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < ntiles; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < ntiles ? cnt[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int tt = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += tt;
+        }
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int ss = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int tt = __shfl_up_sync(0xffffffffu, ss, o);
+                if (lane >= o) ss += tt;
+            }
+            wsum[lane] = ss;
+        }
+        __syncthreads();
+        if (i < ntiles) cnt[i] = carry + (wid ? wsum[wid - 1] : 0) + incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry += wsum[31];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) active_scatter_kernel(ColView c, AssocWork w) {
+    if (w.act_n[2]) return;
+    const int n = *c.n_ptr;
+    const int ntiles = (n + 255) / 256;
+    const long long plane = (long long)(ntiles + 1);
+    const int q = w.act_n[1];
+    __shared__ int wsum[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int j = tile * 256 + threadIdx.x;
+        const int f = (j < n && (active_mask(c, w, j) & (1 << q))) ? 1 : 0;
+        const unsigned b = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wsum[wid] = __popc(b);
+        __syncthreads();
+        int before = __popc(b & ((1u << lane) - 1));
+        for (int k = 0; k < wid; ++k) before += wsum[k];
+        if (f) w.act_col[w.act_tile[q * plane + tile] + before] = j;
+        __syncthreads();
+    }
+}
+
+// between sifting rounds: continue from the best multipliers, re-arm the iteration
+__global__ void __launch_bounds__(1024, 1) sift_rearm_kernel(ColView c, AssocWork w) {
+    for (int r = threadIdx.x; r < c.n_rows; r += blockDim.x) w.u[r] = w.best_u[r];
+    for (int t = threadIdx.x; t < c.n_trees; t += blockDim.x) {
+        w.tmin[t] = kKeyInf;
+        w.targ[t] = -1;
+        if (w.uf[t] == t && !w.cl_done[t]) {
+            w.cl_best[t] = -1e300;   // bounds from a restricted column set are not comparable across rounds
+            w.cl_stall[t] = 0;
+        }
+    }
+    if (threadIdx.x == 0) {
+        w.info[0] = 0;
+        w.stall_ctr[0] = 0;
+    }
+}
+
+__global__ void reset_tree_min_kernel(int T, AssocWork w) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+        w.tmin[t] = kKeyInf;
+        w.targ[t] = -1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // final bound, candidates, components, exact search
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1) final_prepare_kernel(ColView c, AssocWork w) {
@@ -513,9 +687,20 @@ __device__ __forceinline__ bool is_candidate(const ColView &c, const AssocWork &
 
 __global__ void __launch_bounds__(256) cand_count_kernel(ColView c, AssocWork w) {
     const int n = *c.n_ptr;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        const int t = c.tree[j];
-        if (is_candidate(c, w, j, t)) atomicAdd(&w.cand_cnt[t], 1);
+    const int nround = (n + 31) & ~31;
+    const int lane = threadIdx.x & 31;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += gridDim.x * blockDim.x) {
+        const int t = j < n ? c.tree[j] : -1;
+        int v = (j < n && is_candidate(c, w, j, t)) ? 1 : 0;
+        // sum over runs of equal tree inside the warp, one atomic per run
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int ov = __shfl_down_sync(0xffffffffu, v, o);
+            const int ot = __shfl_down_sync(0xffffffffu, t, o);
+            if (lane + o < 32 && ot == t) v += ov;
+        }
+        const int pt = __shfl_up_sync(0xffffffffu, t, 1);
+        if ((lane == 0 || pt != t) && t >= 0 && v) atomicAdd(&w.cand_cnt[t], v);
     }
 }
 
@@ -807,6 +992,8 @@ static int64_t carve_all(Carver &cv, int64_t cap_cols, int64_t T, int64_t R, int
     d.cl_stall = cv.take<int>(T);
     d.cl_done = cv.take<int>(T);
     d.cl_flag = cv.take<int>(T);
+    d.tdone = cv.take<int>(T);
+    d.stall_ctr = cv.take<int>(4);
     d.cand_cnt = cv.take<int>(T + 1);
     d.cand_off = cv.take<int>(T + 1);
     d.cand_fill = cv.take<int>(T + 1);
@@ -821,6 +1008,10 @@ static int64_t carve_all(Carver &cv, int64_t cap_cols, int64_t T, int64_t R, int
     d.row_bid = cv.take<unsigned long long>(R);
     d.row_taken = cv.take<int>(R);
     d.row_mark = cv.take<int>(R);
+    d.cap_act = cap_cols < (1 << 20) ? cap_cols : (cap_cols / 8 > (1 << 20) ? cap_cols / 8 : (1 << 20));
+    d.act_col = cv.take<int>(d.cap_act);
+    d.act_tile = cv.take<int>(4 * (cap_cols / 256 + 2));
+    d.act_n = cv.take<int>(4);
     d.cand_col = cv.take<int>(cap_cand);
     d.cand_stack = cv.take<int>(3 * T + 8);
     d.cap_cand = cap_cand;
@@ -849,11 +1040,12 @@ void assoc_carve(void *d_work, int64_t cap_cols, int64_t T, int64_t R, int64_t c
     carve_all(cv, cap_cols, T, R, cap_cand, w, &g_tstart, &g_tend, &g_fscratch);
 }
 
-static int cluster_phase(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s) {
+static int cluster_phase(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s, bool warm = false) {
     const int T = c.n_trees;
     assoc_clear_ranges_kernel<<<(T + 255) / 256, 256, 0, s>>>(T, g_tstart, g_tend);
-    assoc_init_kernel<<<grid_dim, 256, 0, s>>>(c, w, g_tstart, g_tend);
-    uf_union_cols_kernel<<<grid_dim, 256, 0, s>>>(c, w.uf, w.row_owner);
+    assoc_init_kernel<<<grid_dim, 256, 0, s>>>(c, w, g_tstart, g_tend, warm ? 1 : 0);
+    uf_union_cols_kernel<<<grid_dim, 256, 0, s>>>(c, w.uf, w.row_owner, w.row_mark);
+    if (warm) warm_fix_kernel<<<(c.n_rows + 255) / 256, 256, 0, s>>>(c.n_rows, w.row_mark, w.u, w.best_u);
     uf_flatten_kernel<<<(T + 255) / 256, 256, 0, s>>>(T, w.uf);
     cluster_stats_kernel<<<1, 1024, 0, s>>>(T, w.uf, g_tstart, w.cl_nrm, w.info);
     MHT_CUDA(cudaGetLastError());
@@ -874,23 +1066,43 @@ static void greedy_pass(const ColView &c, AssocWork &w, int grid_dim, cudaStream
     greedy_finish_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
 }
 
+static void dual_loop(const ColView &c, AssocWork &w, int iters, int grid_dim, cudaStream_t s) {
+    for (int it = 0; it < iters; ++it) {
+        if (it % kGreedyEvery == 0) {
+            dual_rc_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);  // rc at the current multipliers
+            greedy_pass(c, w, grid_dim, s);
+        }
+        dual_rc_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
+        dual_arg_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
+        dual_update_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
+    }
+}
+
 int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, int grid_dim, cudaStream_t s,
-                cudaEvent_t after_cluster) {
-    if (int rc = cluster_phase(c, w, grid_dim, s)) return rc;
+                cudaEvent_t after_cluster, bool warm_start, bool sift) {
+    if (int rc = cluster_phase(c, w, grid_dim, s, warm_start)) return rc;
     if (after_cluster) MHT_CUDA(cudaEventRecord(after_cluster, s));
     // iteration 0 settles every conflict-free cluster (all singletons) exactly
     dual_rc_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
     dual_arg_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
     dual_update_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
-    for (int it = 0; it < max_iters; ++it) {
-        if (it % kGreedyEvery == 0) {
-            dual_rc_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);  // rc at the current multipliers
-            greedy_pass(c, w, grid_dim, s);
-            // dual_rc left tmin populated; dual_update below consumes a fresh pass anyway
+    if (!sift) {
+        dual_loop(c, w, max_iters, grid_dim, s);
+    } else {
+        // sifting: price all columns, iterate on the active list, re-price; kSiftRounds times
+        ColView a = c;
+        a.idx = w.act_col;
+        a.n_ptr = w.act_n;
+        const int act_grid = grid_dim < kSMs * 2 ? grid_dim : kSMs * 2;
+        for (int round = 0; round < kSiftRounds; ++round) {
+            if (round) sift_rearm_kernel<<<1, 1024, 0, s>>>(c, w);
+            dual_rc_kernel<true><<<grid_dim, 256, 0, s>>>(c, w);
+            active_count_kernel<<<grid_dim, 256, 0, s>>>(c, w);
+            active_scan_kernel<<<1, 1024, 0, s>>>(c, w);
+            active_scatter_kernel<<<grid_dim, 256, 0, s>>>(c, w);
+            reset_tree_min_kernel<<<(c.n_trees + 255) / 256, 256, 0, s>>>(c.n_trees, w);
+            dual_loop(a, w, max_iters, act_grid, s);
         }
-        dual_rc_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
-        dual_arg_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
-        dual_update_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
     }
     MHT_CUDA(cudaGetLastError());
     // final multipliers -> reduced costs, bound, candidates, exact repair
@@ -932,6 +1144,7 @@ static int make_view(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t wi
     MHT_CUDA(cudaMemcpyAsync(n_dev, &n32, sizeof(int), cudaMemcpyHostToDevice, s));
     assoc_carve((char *)d_work + 256, n_cols, n_trees, n_rows, n_cols, w);
     c->n_ptr = n_dev;
+    c->idx = nullptr;
     c->cost = d_cost;
     c->tree_base = nullptr;
     c->tree = d_tree;
@@ -965,7 +1178,7 @@ extern "C" int mht_assoc_solve(int64_t n_cols, int64_t n_trees, int64_t n_rows, 
     AssocWork w;
     if (int rc = make_view(n_cols, n_trees, n_rows, width, d_col_cost, d_col_tree, d_col_rows, d_work, &c, &w, s))
         return rc;
-    if (int rc = assoc_solve(c, w, 200, 2000000, kSMs * 4, s)) return rc;
+    if (int rc = assoc_solve(c, w, 200, 2000000, kSMs * 4, s, nullptr, false, n_cols > 2000000)) return rc;
     MHT_CUDA(cudaMemcpyAsync(d_selected_col, w.sel, n_trees * sizeof(int), cudaMemcpyDeviceToDevice, s));
     int info[kAssocInfo];
     double obj[2];

@@ -9,7 +9,8 @@ constexpr int kAssocInfo = 16;  // ints in AssocWork::info
 
 // Column view: one column = one leaf hypothesis.  Columns of a tree are contiguous.
 struct ColView {
-    const int *n_ptr;          // device scalar: number of columns
+    const int *n_ptr;          // device scalar: number of columns (entries of idx when idx != null)
+    const int *idx;            // null, or ascending list of ACTIVE column indices (sifting)
     const double *cost;        // [n]   (cumulative NLLR for the forest)
     const double *tree_base;   // [T] or null: cost_j := cost[j] - tree_base[tree[j]]
     const int *tree;           // [n] non-decreasing
@@ -36,6 +37,8 @@ struct AssocWork {
     int *cl_nrm;
     double *cl_best, *cl_ub, *cl_theta, *cl_step;
     int *cl_stall, *cl_done, *cl_flag;
+    int *tdone;                // [T] cl_done of the tree's cluster (one load, not a uf -> cl_done chain)
+    int *stall_ctr;            // [4] iterations without any bound improvement
     int *cand_cnt, *cand_off, *cand_fill;   // [T+1]
     int *comp_uf, *comp_trees, *comp_off, *comp_cnt;  // candidate components
     // per row
@@ -46,6 +49,10 @@ struct AssocWork {
     int *row_taken;
     int *row_mark;
     // candidates
+    int *act_col;              // [cap_act] active column list (sifting)
+    int *act_tile;             // [4][cap_cols/256+2] per-tile counts for 4 thresholds
+    int *act_n;                // [4] device: list length, chosen threshold index
+    long long cap_act;
     int *cand_col;             // [cap_cand]
     int *cand_stack;           // [T] DFS cursors, [T] order etc. carved by the kernel
     long long cap_cand;
@@ -62,6 +69,6 @@ void assoc_carve(void *d_work, int64_t cap_cols, int64_t n_trees, int64_t n_rows
 int assoc_cluster(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s);
 // full solve; async; results in w.sel / w.info / w.objective
 int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, int grid_dim, cudaStream_t s,
-                cudaEvent_t after_cluster = nullptr);
+                cudaEvent_t after_cluster = nullptr, bool warm_start = false, bool sift = false);
 
 }  // namespace mht

@@ -15,13 +15,15 @@
 #include <new>
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 
 #include "assoc.cuh"
 
 namespace mht {
 
 struct Level {
-    double *x;       // [cap_nodes][4]
+    double2 *xa;     // [cap_nodes] (x, y)
+    double2 *xb;     // [cap_nodes] (vx, vy)
     double *cnllr;   // [cap_nodes]
     int *meas;       // [cap_nodes]  measurementNumber (0 = miss / initial)
     int *pidx;       // [cap_nodes]  index into this level's Pbar/Phat tables
@@ -164,8 +166,7 @@ __device__ __forceinline__ void locate(const ScanArgs &a, int i, int &t, int &po
 }
 
 __device__ __forceinline__ void load_leaf(const ScanArgs &a, int pos, double x0[4], float P0[16]) {
-    const double2 *xp = (const double2 *)(a.prev.x + 4 * (size_t)pos);
-    const double2 x01 = xp[0], x23 = xp[1];
+    const double2 x01 = a.prev.xa[pos], x23 = a.prev.xb[pos];
     x0[0] = x01.x;
     x0[1] = x01.y;
     x0[2] = x23.x;
@@ -263,31 +264,39 @@ __global__ void __launch_bounds__(1024, 1) forest_scan_tiles_kernel(ScanArgs a) 
     }
 }
 
-__device__ __forceinline__ void sort_run_global(int *v, int n) {
-    for (int i = 1; i < n; ++i) {
-        const int key = v[i];
-        int j = i - 1;
-        while (j >= 0 && v[j] > key) {
-            v[j + 1] = v[j];
-            --j;
-        }
-        v[j + 1] = key;
-    }
-}
-
 // pass 2: write the new level.  Child order per leaf = [miss, gated by ascending measurement index]
 // (Target.spawnNewNodes, pyTarget.py:239-254).
-__global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a) {
+//   phase A (one thread per live leaf): Kalman quantities -> shared memory, P_bar/P_hat -> HBM, gated
+//            measurement indices (grid order) -> scratch at the leaf's child offset;
+//   phase B (one thread per CHILD, consecutive threads = consecutive children): rank the measurement
+//            among its siblings (ascending index), filter, score, and store every field coalesced.
+constexpr int kEmitD = 13;  // doubles per leaf in smem: xbar[4] zhat[2] si[4] logterm miss_cnllr base_cnllr
+__host__ __device__ inline size_t emit_smem_bytes(int W) {
+    return (size_t)kTile * (kEmitD * 8 + 8 * 4 + 4 + 4 * W) + 264 * 4;
+}
+
+__global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, int *scratch) {
     if (a.status->overflow) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_d = (double *)smem_raw;                 // [kEmitD][kTile]
+    float *s_K = (float *)(s_d + kEmitD * kTile);      // [8][kTile]
+    int *s_tree = (int *)(s_K + 8 * kTile);            // [kTile]
+    int *s_off = s_tree + kTile;                       // [kTile+1] child offsets inside the tile
+    int *s_path = s_off + 264;                         // [W][kTile]
     const int np = *a.d_np;
     const int ntiles = (np + kTile - 1) / kTile;
     const int plane_cur = a.scan % a.W;
+    const int tid = threadIdx.x;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int i = tile * kTile + threadIdx.x;
+        const int i = tile * kTile + tid;
         const int cnt = (i < np) ? a.count[i] : 0;
-        const int off = a.tile_sum[tile] + block_scan_excl(cnt, nullptr);
+        int total;
+        const int loc = block_scan_excl(cnt, &total);
+        const int tile_base = a.tile_sum[tile];
+        s_off[tid] = loc;
+        if (tid == 0) s_off[kTile] = total;
         if (i < np) {
-            a.count[i] = off;  // child offset, read back by tree_off_kernel
+            a.count[i] = tile_base + loc;  // child offset, read back by tree_off_kernel
             int t, pos;
             locate(a, i, t, pos);
             double x0[4];
@@ -302,51 +311,80 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a) {
                 ph[r] = make_float4(kf.Phat[4 * r], kf.Phat[4 * r + 1], kf.Phat[4 * r + 2], kf.Phat[4 * r + 3]);
             }
             const double base = a.prev.cnllr[pos];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s_d[q * kTile + tid] = kf.xbar[q];
+            s_d[4 * kTile + tid] = kf.zhat[0];
+            s_d[5 * kTile + tid] = kf.zhat[1];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s_d[(6 + q) * kTile + tid] = kf.si[q];
+            s_d[10 * kTile + tid] = kf.logterm;
+            s_d[11 * kTile + tid] = base + a.ts.miss[t];
+            s_d[12 * kTile + tid] = base;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s_K[q * kTile + tid] = kf.K[q];
+            s_tree[tid] = t;
             // inherited path planes (entries at or above the tree's root are dropped)
-            int path[MHT_MAX_WINDOW];
             const int root_scan = a.ts.root_scan[t];
-#pragma unroll 4
             for (int w = 0; w < a.W; ++w) {
                 const int back = ((a.scan - w) % a.W + a.W) % a.W;  // scans since plane w was written
                 const int s_w = a.scan - back;
-                path[w] = (w != plane_cur && s_w > root_scan) ? a.rows_prev[(long long)w * a.stride + pos] : -1;
+                s_path[w * kTile + tid] =
+                    (w != plane_cur && s_w > root_scan) ? a.rows_prev[(long long)w * a.stride + pos] : -1;
             }
-            // miss child
-            {
-                double2 *xo = (double2 *)(a.cur.x + 4 * (size_t)off);
-                xo[0] = make_double2(kf.xbar[0], kf.xbar[1]);
-                xo[1] = make_double2(kf.xbar[2], kf.xbar[3]);
-                a.cur.cnllr[off] = base + a.ts.miss[t];
-                a.cur.meas[off] = 0;
-                a.cur.pidx[off] = i;
-                a.cur.tree[off] = t;
-                for (int w = 0; w < a.W; ++w) a.rows_cur[(long long)w * a.stride + off] = path[w];
-            }
-            // gated children: collect indices, sort ascending, then fill
             int k = 0;
-            int *mdst = a.cur.meas + off + 1;
+            int *dst = scratch + tile_base + loc + 1;
             for_each_gated(*a.grid, a.cell_start, a.gz, kf, a.model.eta2,
-                           [&](int p, double, double, double) { mdst[k++] = a.gidx[p]; });
-            sort_run_global(mdst, cnt - 1);
-            for (k = 0; k < cnt - 1; ++k) {
-                const int m = mdst[k];
-                const int c = off + 1 + k;
+                           [&](int p, double, double, double) { dst[k++] = a.gidx[p]; });
+        }
+        __syncthreads();
+        for (int c = tid; c < total; c += kTile) {
+            int lo = 0, hi = kTile;  // parent = largest p with s_off[p] <= c
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_off[mid] <= c) lo = mid; else hi = mid;
+            }
+            const int p = lo;
+            const int k = c - s_off[p];
+            const int first = tile_base + s_off[p];
+            const int t = s_tree[p];
+            int g, row_new, mnum;
+            double xo0, xo1, xo2, xo3, cn;
+            if (k == 0) {
+                g = first;
+                row_new = -1;
+                mnum = 0;
+                xo0 = s_d[0 * kTile + p];
+                xo1 = s_d[1 * kTile + p];
+                xo2 = s_d[2 * kTile + p];
+                xo3 = s_d[3 * kTile + p];
+                cn = s_d[11 * kTile + p];
+            } else {
+                const int nsib = s_off[p + 1] - s_off[p] - 1;
+                const int m = scratch[first + k];
+                int rank = 0;
+                for (int q = 1; q <= nsib; ++q) rank += scratch[first + q] < m;
+                g = first + 1 + rank;
+                row_new = plane_cur * a.max_meas + m;
+                mnum = m + 1;
                 const double2 z = a.z[m];
-                const double v0 = z.x - kf.zhat[0], v1 = z.y - kf.zhat[1];
-                const double d2 = nis_f64(kf.si, v0, v1);
-                double xh[4];
-                filter_f64(kf, v0, v1, xh);
-                double2 *xo = (double2 *)(a.cur.x + 4 * (size_t)c);
-                xo[0] = make_double2(xh[0], xh[1]);
-                xo[1] = make_double2(xh[2], xh[3]);
-                a.cur.cnllr[c] = base + (0.5 * d2 + kf.logterm);
-                a.cur.meas[c] = m + 1;
-                a.cur.pidx[c] = i;
-                a.cur.tree[c] = t;
-                for (int w = 0; w < a.W; ++w)
-                    a.rows_cur[(long long)w * a.stride + c] = (w == plane_cur) ? plane_cur * a.max_meas + m : path[w];
+                const double v0 = z.x - s_d[4 * kTile + p], v1 = z.y - s_d[5 * kTile + p];
+                const double si[4] = {s_d[6 * kTile + p], s_d[7 * kTile + p], s_d[8 * kTile + p], s_d[9 * kTile + p]};
+                const double d2 = nis_f64(si, v0, v1);
+                xo0 = s_d[0 * kTile + p] + fma((double)s_K[1 * kTile + p], v1, (double)s_K[0 * kTile + p] * v0);
+                xo1 = s_d[1 * kTile + p] + fma((double)s_K[3 * kTile + p], v1, (double)s_K[2 * kTile + p] * v0);
+                xo2 = s_d[2 * kTile + p] + fma((double)s_K[5 * kTile + p], v1, (double)s_K[4 * kTile + p] * v0);
+                xo3 = s_d[3 * kTile + p] + fma((double)s_K[7 * kTile + p], v1, (double)s_K[6 * kTile + p] * v0);
+                cn = s_d[12 * kTile + p] + (0.5 * d2 + s_d[10 * kTile + p]);
                 a.used[m] = 1;
             }
+            a.cur.xa[g] = make_double2(xo0, xo1);
+            a.cur.xb[g] = make_double2(xo2, xo3);
+            a.cur.cnllr[g] = cn;
+            a.cur.meas[g] = mnum;
+            a.cur.pidx[g] = tile * kTile + p;
+            a.cur.tree[g] = t;
+            for (int w = 0; w < a.W; ++w)
+                a.rows_cur[(long long)w * a.stride + g] = (w == plane_cur) ? row_new : s_path[w * kTile + p];
         }
         __syncthreads();
     }
@@ -406,7 +444,10 @@ __global__ void track_update_kernel(UpdateArgs a) {
     const int sel = a.sel[t];
     const double cn = cur.cnllr[sel];
     double x[4];
-    for (int i = 0; i < 4; ++i) x[i] = cur.x[4 * (size_t)sel + i];
+    {
+        const double2 p01 = cur.xa[sel], p23 = cur.xb[sel];
+        x[0] = p01.x; x[1] = p01.y; x[2] = p23.x; x[3] = p23.y;
+    }
     const int meas = cur.meas[sel];
     a.out.pos[t] = sel;
     a.out.meas[t] = meas;
@@ -449,7 +490,11 @@ __global__ void track_update_kernel(UpdateArgs a) {
         a.out.advanced[t] = root_new - root_old;
         a.out.root_meas[t] = LR.meas[pos];
         a.out.root_cnllr[t] = LR.cnllr[pos];
-        for (int i = 0; i < 4; ++i) a.out.root_x[4 * t + i] = LR.x[4 * (size_t)pos + i];
+        {
+            const double2 p01 = LR.xa[pos], p23 = LR.xb[pos];
+            a.out.root_x[4 * t] = p01.x; a.out.root_x[4 * t + 1] = p01.y;
+            a.out.root_x[4 * t + 2] = p23.x; a.out.root_x[4 * t + 3] = p23.y;
+        }
         const float *tab = (LR.meas[pos] ? LR.Phat : LR.Pbar) + 16 * (size_t)LR.pidx[pos];
         for (int i = 0; i < 16; ++i) a.out.root_P[16 * t + i] = tab[i];
         // contiguous range of leaves whose path agrees with the selected leaf on (root_old, root_new]
@@ -482,7 +527,10 @@ __global__ void history_kernel(UpdateArgs a, int t, int pos, int scan_from, doub
         double *o = out + kHistRec + kHistRec * n++;
         o[0] = (double)L.meas[pos];
         o[1] = L.cnllr[pos];
-        for (int i = 0; i < 4; ++i) o[2 + i] = L.x[4 * (size_t)pos + i];
+        {
+            const double2 p01 = L.xa[pos], p23 = L.xb[pos];
+            o[2] = p01.x; o[3] = p01.y; o[4] = p23.x; o[5] = p23.y;
+        }
         o[6] = (double)s;
         const float *tab = (L.meas[pos] ? L.Phat : L.Pbar) + 16 * (size_t)L.pidx[pos];
         for (int i = 0; i < 16; ++i) o[8 + i] = (double)tab[i];
@@ -499,7 +547,8 @@ __global__ void min_leaf_distance_kernel(Level cur, TreeState ts, int T, double 
     for (int t = blockIdx.x; t < T; t += gridDim.x) {
         if (!ts.alive[t]) continue;
         for (int p = ts.live_lo[t] + threadIdx.x; p < ts.live_hi[t]; p += blockDim.x) {
-            const double dx = cur.x[4 * (size_t)p] - px, dy = cur.x[4 * (size_t)p + 1] - py;
+            const double2 q = cur.xa[p];
+            const double dx = q.x - px, dy = q.y - py;
             const unsigned long long k = f64_key(sqrt(dx * dx + dy * dy));
             best = k < best ? k : best;
         }
@@ -543,7 +592,8 @@ static int forest_layout(mht_forest *f, bool commit) {
     char *p0 = p;
     for (int s = 0; s < f->nslots; ++s) {
         Level &L = f->lv[s];
-        L.x = carve<double>(p, 4 * cn);
+        L.xa = carve<double2>(p, cn);
+        L.xb = carve<double2>(p, cn);
         L.cnllr = carve<double>(p, cn);
         L.meas = carve<int>(p, cn);
         L.pidx = carve<int>(p, cn);
@@ -660,7 +710,7 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     if (int rc = launch_grid_build(d_z, (int)M, grid, cell_start, cell_fill, gz, gidx, s)) return rc;
     forest_count_kernel<<<grid_dim, kTile, 0, s>>>(a);
     forest_scan_tiles_kernel<<<1, 1024, 0, s>>>(a);
-    forest_emit_kernel<<<grid_dim, kTile, 0, s>>>(a);
+    forest_emit_kernel<<<grid_dim, kTile, emit_smem_bytes(f->W), s>>>(a, (int *)f->aw.rc);
     tree_off_kernel<<<(f->T + 256) / 256, 256, 0, s>>>(a);
     MHT_CUDA(cudaGetLastError());
     MHT_CUDA(cudaEventRecord(f->ev[1], s));
@@ -668,6 +718,7 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     f->scan = k;
     ColView c;
     c.n_ptr = f->d_nc;
+    c.idx = nullptr;
     c.cost = a.cur.cnllr;
     c.tree_base = f->ts.root_cnllr;
     c.tree = a.cur.tree;
@@ -678,7 +729,13 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     c.n_rows = f->W * f->cfg.max_meas;
     assoc_carve(f->assoc_ws, f->cap_nodes, f->cfg.max_trees, (int64_t)f->W * f->cfg.max_meas, f->aw.cap_cand,
                 &f->aw);
-    if (int rc = assoc_solve(c, f->aw, f->cfg.max_dual_iters, 400000, kSMs * 8, s, f->ev[5])) return rc;
+    // warm start: measurement rows keep their ids for W scans, so last scan's multipliers are a good
+    // starting point; the plane being recycled for this scan starts from zero
+    MHT_CUDA(cudaMemsetAsync(f->aw.u + (size_t)(k % f->W) * f->cfg.max_meas, 0, sizeof(double) * f->cfg.max_meas, s));
+    static const long long sift_min = getenv("MHT_SIFT_MIN") ? atoll(getenv("MHT_SIFT_MIN")) : 1000000;
+    const bool sift = f->h_level_nodes > sift_min;  // last scan's hypothesis count is the size hint
+    if (int rc = assoc_solve(c, f->aw, f->cfg.max_dual_iters, 400000, kSMs * 8, s, f->ev[5], f->scan > 1, sift))
+        return rc;
     MHT_CUDA(cudaEventRecord(f->ev[2], s));
 
     UpdateArgs u;
@@ -789,6 +846,9 @@ extern "C" int mht_forest_create(const mht_forest_config *cfg, mht_forest **out)
     if (e == cudaSuccess) e = cudaMallocHost(&f->hist_h, kHistRec * sizeof(double) * (MHT_MAX_WINDOW + 4));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&f->ev[i]);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(forest_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)emit_smem_bytes(MHT_MAX_WINDOW));
     if (e == cudaSuccess) e = cudaMemsetAsync(f->ts.alive, 0, sizeof(int) * T, f->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(f->rows[0], 0xff, sizeof(int) * (size_t)f->W * f->cap_nodes, f->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
@@ -844,7 +904,8 @@ extern "C" int mht_forest_initiate(mht_forest *f, const double x0[4], const floa
     const double cn = 0.0, miss = -log(1.0 - Pd);
     int minus[MHT_MAX_WINDOW];
     for (int i = 0; i < MHT_MAX_WINDOW; ++i) minus[i] = -1;
-    MHT_CUDA(cudaMemcpyAsync(L.x + 4 * (size_t)pos, x0, 32, cudaMemcpyHostToDevice, s));
+    MHT_CUDA(cudaMemcpyAsync(L.xa + pos, x0, 16, cudaMemcpyHostToDevice, s));
+    MHT_CUDA(cudaMemcpyAsync(L.xb + pos, x0 + 2, 16, cudaMemcpyHostToDevice, s));
     MHT_CUDA(cudaMemcpyAsync(L.cnllr + pos, &cn, 8, cudaMemcpyHostToDevice, s));
     MHT_CUDA(cudaMemcpyAsync(L.meas + pos, &zero, 4, cudaMemcpyHostToDevice, s));
     MHT_CUDA(cudaMemcpyAsync(L.pidx + pos, &pi, 4, cudaMemcpyHostToDevice, s));
@@ -1008,7 +1069,10 @@ extern "C" int mht_forest_leaves(mht_forest *f, int32_t slot, int64_t cap, int64
     }
     if (cnt == 0) return MHT_OK;
     const Level &L = f->lv[f->scan % f->nslots];
-    if (h_x) MHT_CUDA(cudaMemcpyAsync(h_x, L.x + 4 * (size_t)lohi[0], 32 * cnt, cudaMemcpyDeviceToHost, f->stream));
+    if (h_x) {  // two planes -> interleaved [n][4]
+        MHT_CUDA(cudaMemcpy2DAsync(h_x, 32, L.xa + lohi[0], 16, 16, (size_t)cnt, cudaMemcpyDeviceToHost, f->stream));
+        MHT_CUDA(cudaMemcpy2DAsync(h_x + 2, 32, L.xb + lohi[0], 16, 16, (size_t)cnt, cudaMemcpyDeviceToHost, f->stream));
+    }
     if (h_cnllr) MHT_CUDA(cudaMemcpyAsync(h_cnllr, L.cnllr + lohi[0], 8 * cnt, cudaMemcpyDeviceToHost, f->stream));
     if (h_meas) MHT_CUDA(cudaMemcpyAsync(h_meas, L.meas + lohi[0], 4 * cnt, cudaMemcpyDeviceToHost, f->stream));
     MHT_CUDA(cudaStreamSynchronize(f->stream));
