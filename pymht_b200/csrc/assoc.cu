@@ -88,6 +88,10 @@ __global__ void assoc_init_kernel(ColView c, AssocWork w, int *tstart, int *tend
             w.cl_done[i] = 0;
             w.cl_flag[i] = 0;
             w.tdone[i] = 0;
+            w.cl_m[i] = 0;
+            w.cl_u[i] = 0;
+            w.cl_cost[i] = 0;
+            w.cl_nrm[i] = 0;
         }
         if (i <= T) w.cand_cnt[i] = 0;
         if (i < R) {
@@ -97,7 +101,10 @@ __global__ void assoc_init_kernel(ColView c, AssocWork w, int *tstart, int *tend
             w.best_u[i] = warm ? w.u[i] : 0.0;
             w.usage[i] = 0;
         }
-        if (i < 4) w.stall_ctr[i] = 0;
+        if (i < 4) {
+            w.stall_ctr[i] = 0;
+            w.row_n[i] = 0;
+        }
         if (i < kAssocInfo) w.info[i] = 0;
         if (i == 0) {
             *w.bb_nodes = 0ull;
@@ -144,6 +151,11 @@ __global__ void uf_union_cols_kernel(ColView c, int *uf, int *row_owner, int *ro
 __global__ void warm_fix_kernel(int R, const int *row_multi, double *u, double *best_u) {
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x)
         if (!row_multi[r]) u[r] = best_u[r] = 0.0;
+}
+
+__global__ void row_list_kernel(int R, const int *row_owner, int *row_list, int *row_n) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x)
+        if (row_owner[r] >= 0) row_list[atomicAdd(row_n, 1)] = r;
 }
 
 __global__ void uf_flatten_kernel(int T, int *uf) {
@@ -229,26 +241,16 @@ __global__ void __launch_bounds__(256) dual_arg_kernel(ColView c, AssocWork w) {
     }
 }
 
-// single CTA: subgradient, per-cluster Polyak step, bookkeeping (see file header)
-__global__ void __launch_bounds__(1024, 1) dual_update_kernel(ColView c, AssocWork w, const int *tstart) {
-    if (w.info[0]) return;
-    if (c.idx && w.act_n[2]) {  // the active list did not fit: nothing to iterate on
-        if (threadIdx.x == 0) w.info[0] = 1;
-        return;
-    }
-    const int T = c.n_trees, R = c.n_rows;
-    __shared__ int open;
-    if (threadIdx.x == 0) open = 0;
-    for (int t = threadIdx.x; t < T; t += blockDim.x) {
-        w.cl_m[t] = 0;
-        w.cl_u[t] = 0;
-        w.cl_cost[t] = 0;
-        w.cl_nrm[t] = 0;
-        w.cl_flag[t] = 0;
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < T; t += blockDim.x) {
-        if (tstart[t] < 0) continue;
+// subgradient, per-cluster Polyak step and bookkeeping, as four small grid kernels
+// (accumulators cl_m/cl_u/cl_cost/cl_nrm are zero on entry: assoc_init / du_apply leave them so)
+__device__ __forceinline__ bool du_skip(const ColView &c, const AssocWork &w) {
+    return w.info[0] || (c.idx && w.act_n[2]);
+}
+
+__global__ void du_trees_kernel(ColView c, AssocWork w) {
+    if (du_skip(c, w)) return;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
+        if (w.tstart[t] < 0) continue;
         const int cl = w.uf[t];
         if (w.cl_done[cl]) continue;
         const int j = w.targ[t];
@@ -259,11 +261,14 @@ __global__ void __launch_bounds__(1024, 1) dual_update_kernel(ColView c, AssocWo
             if (r >= 0) atomicAdd(&w.usage[r], 1);
         }
     }
-    __syncthreads();
-    for (int r = threadIdx.x; r < R; r += blockDim.x) {
-        const int o = w.row_owner[r];
-        if (o < 0) continue;
-        const int cl = w.uf[o];
+}
+
+__global__ void du_rows_kernel(ColView c, AssocWork w) {
+    if (du_skip(c, w)) return;
+    const int nr = *w.row_n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += gridDim.x * blockDim.x) {
+        const int r = w.row_list[i];
+        const int cl = w.uf[w.row_owner[r]];
         if (w.cl_done[cl]) continue;
         int g = w.usage[r] - 1;
         const double ur = w.u[r];
@@ -272,9 +277,12 @@ __global__ void __launch_bounds__(1024, 1) dual_update_kernel(ColView c, AssocWo
         if (g) atomicAdd(&w.cl_nrm[cl], g * g);
         if (ur > 0.0) atomicAdd((unsigned long long *)&w.cl_u[cl], (unsigned long long)to_fix(ur));
     }
-    __syncthreads();
-    for (int t = threadIdx.x; t < T; t += blockDim.x) {
-        if (tstart[t] < 0 || w.uf[t] != t || w.cl_done[t]) continue;
+}
+
+__global__ void du_decide_kernel(ColView c, AssocWork w) {
+    if (du_skip(c, w)) return;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
+        if (w.tstart[t] < 0 || w.uf[t] != t || w.cl_done[t]) continue;
         const double L = from_fix(w.cl_m[t] - w.cl_u[t]);
         const int nrm = w.cl_nrm[t];
         if (nrm == 0) {  // conflict-free and complementary: argmins are optimal
@@ -283,11 +291,14 @@ __global__ void __launch_bounds__(1024, 1) dual_update_kernel(ColView c, AssocWo
             w.cl_ub[t] = from_fix(w.cl_cost[t]);
             w.cl_flag[t] = 3;
             w.cl_step[t] = 0.0;
+            atomicOr(&w.stall_ctr[2], 1);
             continue;
         }
         if (L > w.cl_best[t] + 1e-12) {
             // flag 1 = keep these multipliers; flag 8 = the gain is large enough to keep iterating
-            w.cl_flag[t] = (L > w.cl_best[t] + 1e-6 * fmax(1.0, fabs(L))) ? 9 : 1;
+            const bool big = L > w.cl_best[t] + 1e-6 * fmax(1.0, fabs(L));
+            w.cl_flag[t] = big ? 9 : 1;
+            if (big) atomicOr(&w.stall_ctr[2], 1);
             w.cl_best[t] = L;
             w.cl_stall[t] = 0;
         } else if (++w.cl_stall[t] >= kPatience) {
@@ -300,38 +311,64 @@ __global__ void __launch_bounds__(1024, 1) dual_update_kernel(ColView c, AssocWo
         } else {
             // no step before the first primal solution provides an upper bound
             w.cl_step[t] = w.cl_ub[t] < 1e299 ? w.cl_theta[t] * (w.cl_ub[t] - L) / (double)nrm : 0.0;
-            atomicAdd(&open, 1);
+            atomicAdd(&w.stall_ctr[1], 1);
         }
     }
-    __syncthreads();
-    for (int r = threadIdx.x; r < R; r += blockDim.x) {
-        const int o = w.row_owner[r];
-        if (o < 0) continue;
-        const int cl = w.uf[o];
+}
+
+__global__ void du_apply_kernel(ColView c, AssocWork w) {
+    if (du_skip(c, w)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && c.idx && w.act_n[2]) w.info[0] = 1;
+        return;
+    }
+    const int nr = *w.row_n;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += stride) {
+        const int r = w.row_list[i];
+        const int cl = w.uf[w.row_owner[r]];
         const int fl = w.cl_flag[cl];
         if (fl & 1) w.best_u[r] = w.u[r];
         if (!w.cl_done[cl]) w.u[r] = fmax(0.0, w.u[r] + w.cl_step[cl] * (double)w.usage[r]);
         w.usage[r] = 0;
     }
-    __shared__ int improved;
-    if (threadIdx.x == 0) improved = 0;
-    __syncthreads();
-    for (int t = threadIdx.x; t < T; t += blockDim.x) {
-        if (tstart[t] < 0) continue;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += stride) {
+        if (w.tstart[t] < 0) continue;
         const int cl = w.uf[t];
         if (w.cl_flag[cl] & 2) w.sel[t] = w.targ[t];
-        if (w.cl_flag[cl] & (8 | 2)) improved = 1;
         w.tdone[t] = w.cl_done[cl];
         w.tmin[t] = kKeyInf;
         w.targ[t] = -1;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+}
+
+// runs after du_apply: clears the per-cluster accumulators/flags and advances the iteration state
+__global__ void du_finish_kernel(ColView c, AssocWork w) {
+    if (w.info[0]) return;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
+        w.cl_m[t] = 0;
+        w.cl_u[t] = 0;
+        w.cl_cost[t] = 0;
+        w.cl_nrm[t] = 0;
+        w.cl_flag[t] = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         w.info[1] += 1;
         // stop when every cluster is settled, or no bound moved noticeably for kStallStop iterations
-        w.stall_ctr[0] = improved ? 0 : w.stall_ctr[0] + 1;
-        if (open == 0 || w.stall_ctr[0] >= kStallStop) w.info[0] = 1;
+        w.stall_ctr[0] = w.stall_ctr[2] ? 0 : w.stall_ctr[0] + 1;
+        if (w.stall_ctr[1] == 0 || w.stall_ctr[0] >= kStallStop) w.info[0] = 1;
+        w.stall_ctr[1] = 0;
+        w.stall_ctr[2] = 0;
     }
+}
+
+static void dual_update(const ColView &c, AssocWork &w, cudaStream_t s) {
+    const int tb = (c.n_trees + 127) / 128;
+    const int rb = tb > 64 ? tb : 64;
+    du_trees_kernel<<<tb, 128, 0, s>>>(c, w);
+    du_rows_kernel<<<rb, 256, 0, s>>>(c, w);
+    du_decide_kernel<<<tb, 128, 0, s>>>(c, w);
+    du_apply_kernel<<<rb, 256, 0, s>>>(c, w);
+    du_finish_kernel<<<tb, 128, 0, s>>>(c, w);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -471,6 +508,11 @@ __global__ void __launch_bounds__(1024, 1) greedy_finish_kernel(ColView c, Assoc
         if (tstart[t] < 0) continue;
         if (w.cl_flag[w.uf[t]] & 4) w.sel[t] = w.sel_new[t];
     }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {  // leave the dual-update accumulators clean
+        w.cl_cost[t] = 0;
+        w.cl_flag[t] = 0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -484,11 +526,9 @@ __device__ __forceinline__ int active_mask(const ColView &c, const AssocWork &w,
     const int t = c.tree[j];
     if (w.tdone[t]) return 0;
     const double exc = w.rc[j] - key_f64(w.tmin[t]);
-    bool keep = j == w.sel[t];
-    if (!keep) {  // a column without rows can always be chosen: keeps the restricted problem feasible
-        keep = true;
-        for (int k = 0; k < c.width; ++k) keep = keep && c.rows[(long long)k * c.stride + j] < 0;
-    }
+    // the first column of a tree is its all-miss leaf (the miss child is the first child at every level):
+    // it uses no row, so it keeps the restricted problem feasible; the incumbent stays in as well
+    const bool keep = j == w.sel[t] || j == w.tstart[t];
     int m = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) m |= (keep || exc <= kActDelta[q]) ? (1 << q) : 0;
@@ -1008,6 +1048,8 @@ static int64_t carve_all(Carver &cv, int64_t cap_cols, int64_t T, int64_t R, int
     d.row_bid = cv.take<unsigned long long>(R);
     d.row_taken = cv.take<int>(R);
     d.row_mark = cv.take<int>(R);
+    d.row_list = cv.take<int>(R);
+    d.row_n = cv.take<int>(4);
     d.cap_act = cap_cols < (1 << 20) ? cap_cols : (cap_cols / 8 > (1 << 20) ? cap_cols / 8 : (1 << 20));
     d.act_col = cv.take<int>(d.cap_act);
     d.act_tile = cv.take<int>(4 * (cap_cols / 256 + 2));
@@ -1020,6 +1062,7 @@ static int64_t carve_all(Carver &cv, int64_t cap_cols, int64_t T, int64_t R, int
     d.objective = cv.take<double>(2);
     int *ts = cv.take<int>(T), *te = cv.take<int>(T);
     double *fs = cv.take<double>(4 * T + 8);
+    d.tstart = ts;
     if (w) *w = d;
     if (tstart) *tstart = ts;
     if (tend) *tend = te;
@@ -1047,6 +1090,7 @@ static int cluster_phase(const ColView &c, AssocWork &w, int grid_dim, cudaStrea
     uf_union_cols_kernel<<<grid_dim, 256, 0, s>>>(c, w.uf, w.row_owner, w.row_mark);
     if (warm) warm_fix_kernel<<<(c.n_rows + 255) / 256, 256, 0, s>>>(c.n_rows, w.row_mark, w.u, w.best_u);
     uf_flatten_kernel<<<(T + 255) / 256, 256, 0, s>>>(T, w.uf);
+    row_list_kernel<<<(c.n_rows + 255) / 256, 256, 0, s>>>(c.n_rows, w.row_owner, w.row_list, w.row_n);
     cluster_stats_kernel<<<1, 1024, 0, s>>>(T, w.uf, g_tstart, w.cl_nrm, w.info);
     MHT_CUDA(cudaGetLastError());
     return MHT_OK;
@@ -1074,7 +1118,7 @@ static void dual_loop(const ColView &c, AssocWork &w, int iters, int grid_dim, c
         }
         dual_rc_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
         dual_arg_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
-        dual_update_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
+        dual_update(c, w, s);
     }
 }
 
@@ -1085,7 +1129,7 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
     // iteration 0 settles every conflict-free cluster (all singletons) exactly
     dual_rc_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
     dual_arg_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
-    dual_update_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
+    dual_update(c, w, s);
     if (!sift) {
         dual_loop(c, w, max_iters, grid_dim, s);
     } else {

@@ -48,6 +48,9 @@ struct AssocWork {
     unsigned long long *row_bid;
     int *row_taken;
     int *row_mark;
+    int *row_list;             // [R] rows touched by at least one column (order irrelevant)
+    int *row_n;                // device: entries of row_list
+    int *tstart;               // [T] first column of each tree (-1: the tree has no columns)
     // candidates
     int *act_col;              // [cap_act] active column list (sifting)
     int *act_tile;             // [4][cap_cols/256+2] per-tile counts for 4 thresholds
