@@ -53,7 +53,7 @@ def make_tracker(name):
     from pymht_b200.tracker import Tracker
     from pymht_b200.models import pv
     nT, R, lam, N, Pd, seed, max_nodes, max_par = WORKLOADS[name]
-    trk = Tracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=16384,
+    trk = Tracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=8192,
                   maxNodes=max_nodes, maxParents=max_par,
                   maxDualIterations=int(os.environ.get("MHT_DUAL_ITERS", "120")))
     trk.mergeThreshold = 0.0
@@ -137,24 +137,48 @@ def run_e2e_leg(name, scans, simList, preroll, warmup, steps):
     return timed, h2d, n_tracks
 
 
-def run_cpu_port(name, budget_s=25.0, max_scans=3):
-    """The oracle port of the reference CPU path on the first scans of the same workload."""
-    from oracle import mht_oracle as mo
+def run_cpu_reference(name, max_scans=2):
+    """The reference's own CPU path on the first scans of the same workload, cold start.
+
+    Preferred: the UNMODIFIED reference installed at baseline/_ref (pip --no-deps --target, see
+    DESIGN.md) driven through its public API (Tracker.preInitialize / addMeasurementList) under
+    oracle/ref_shim.py, which only stands in for absent third-party modules (matplotlib, termcolor,
+    munkres; OR-Tools CBC -> SciPy HiGHS) and nulls the out-of-scope M-of-N initiator.  Fallback: the
+    oracle port (oracle/mht_oracle.py).  Returns (kind, per-scan seconds of Process+Cluster+Optim+
+    Terminate+N-Prune, leaves after each scan)."""
     nT, R, lam, N, Pd, seed, _, _ = WORKLOADS[name]
     simList, scans = make_scenario(name, max_scans)
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref_root, "pymht")):
+        os.environ["PYMHT_REFERENCE_ROOT"] = ref_root
+        from oracle import ref_shim
+        trk = ref_shim.make_reference_tracker(T_RADAR, lam, 1e-9, N=N, P_d=Pd)
+        from pymht.utils.classDefinitions import MeasurementList as RefScan
+        trk.preInitialize(simList)
+        times, leaves = [], []
+        for s in scans:
+            trk.addMeasurementList(RefScan(s.time, np.asarray(s.measurements)))
+            times.append(sum(trk.toc[k] for k in ("Process", "Cluster", "Optim", "Terminate", "N-Prune")))
+            leaves.append(int(sum(len(t.getLeafNodes()) for t in trk.__targetList__)))
+        return "reference", times, leaves
+    from oracle import mht_oracle as mo
     orc = mo.OracleTracker(T_RADAR, lam, 1e-9, N=N, P_d=Pd)
     for tgt in simList[0]:
         orc.initiate(np.asarray(tgt.cartesianState(), dtype=np.float64), tgt.time)
     times, leaves = [], []
-    t_all = time.perf_counter()
     for s in scans:
         t0 = time.perf_counter()
-        info = orc.add_scan(s.measurements, s.time)
+        orc.add_scan(s.measurements, s.time)
         times.append(time.perf_counter() - t0)
-        leaves.append(info["n_leaves"])
-        if time.perf_counter() - t_all > budget_s:
-            break
-    return times, leaves
+        leaves.append(int(sum(len(l) for l in orc.leaves)))
+    return "port", times, leaves
+
+
+def cpu_sample_text(kind, times, leaves):
+    return ("%s, scans 1-%d of the same scenario from a cold start (leaves after each scan: %s; seconds per scan: %s); "
+            "later scans are out of CPU reach (the reference needs ~160 s for scan 3 and hours beyond)" % (
+                "unmodified reference (baseline/_ref, HiGHS in place of OR-Tools CBC)" if kind == "reference"
+                else "oracle port of the reference", len(times), leaves, [round(t, 2) for t in times]))
 
 
 def main():
@@ -179,15 +203,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        times, leaves = run_cpu_port(name, budget_s=25.0 * max(1, args.steps) / 8.0, max_scans=max(2, min(3, args.steps)))
+        kind, times, leaves = run_cpu_reference(name, max_scans=2)
         v = len(times) / sum(times)
-        sample = "scans 1-%d of the same scenario from a cold start (leaves after each scan: %s); steady-state scans " \
-                 "(millions of leaves) are out of CPU reach" % (len(times), leaves)
         line = {"metric": "scans/sec @ 1k targets, 5k meas/scan", "value": v, "unit": "scans/s", "n_gpus": args.gpus,
                 "steps": len(times), "warmup": 0, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64 state / f32 covariance", "data": "synthetic", "config": config,
                 "impl": "reference",
-                "cpu_baseline": {"value": v, "unit": "scans/s", "cores": 1, "kind": "port", "sample": sample},
+                "cpu_baseline": {"value": v, "unit": "scans/s", "cores": 1, "kind": kind,
+                                 "sample": cpu_sample_text(kind, times, leaves)},
                 "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -263,24 +286,27 @@ def main():
             "forest_hbm_bytes": dev_bytes,
         }
         line["gpu_launches"] = int(sum(launches_per_scan(d) for d in timed))
-        if not args.no_cpu_baseline and world >= 1:
-            times, leaves = run_cpu_port(name)
+        if not args.no_cpu_baseline:
+            kind, times, leaves = run_cpu_reference(name, max_scans=2)
             v = len(times) / sum(times)
-            line["cpu_baseline"] = {"value": v, "unit": "scans/s", "cores": 1, "kind": "port",
-                                    "sample": "oracle port, scans 1-%d of the same scenario from a cold start "
-                                              "(leaves after each scan: %s); the GPU figure is at steady state "
-                                              "(%.2e live leaves/scan)" % (len(times), leaves,
-                                                                           line["scan_stats"]["n_parents"])}
+            line["cpu_baseline"] = {"value": v, "unit": "scans/s", "cores": 1, "kind": kind,
+                                    "sample": cpu_sample_text(kind, times, leaves) +
+                                    "; the GPU figure is at steady state (%.2e live leaves per scan)"
+                                    % line["scan_stats"]["n_parents"]}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
 
 def launches_per_scan(d):
-    """Kernel launches of libmht_b200 per scan (counted from the launch sequence in csrc/)."""
-    iters = 120
+    """Kernel launches of libmht_b200 per scan, counted from the launch sequence in csrc/forest.cu and
+    csrc/assoc.cu (gate 6, cluster 7, settle pass 7, per dual iteration 7, per greedy pass 123, sifting
+    round 6, final 11, track update 1)."""
+    iters = int(os.environ.get("MHT_DUAL_ITERS", "120"))
     greedy = (iters + 39) // 40
-    return 7 + 5 + 3 + 3 * iters + greedy * (1 + 1 + 3 * 40 + 1) + 11 + 1
+    loop = iters * 7 + greedy * (1 + 1 + 3 * 40 + 1)
+    sift = d["n_children"] > 1000000
+    return 6 + 7 + 7 + (3 * (6 + loop) if sift else loop) + 11 + 1
 
 
 if __name__ == "__main__":
