@@ -282,7 +282,7 @@ def main():
                          ("ms_gate", "ms_cluster", "ms_assoc", "ms_prune", "ms_total")},
             "scan_stats": {k: float(np.mean([d[k] for d in timed])) for k in
                            ("n_parents", "n_children", "n_pairs", "n_clusters", "n_multi_clusters", "dual_iters",
-                            "n_candidates", "bb_nodes", "certified", "lower_bound", "objective")},
+                            "n_candidates", "bb_nodes", "certified", "lower_bound", "objective", "n_active")},
             "forest_hbm_bytes": dev_bytes,
         }
         line["gpu_launches"] = int(sum(launches_per_scan(d) for d in timed))

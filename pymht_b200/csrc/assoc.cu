@@ -23,7 +23,11 @@
 //      with the Lagrangian bound.  A finished search certifies optimality.
 // Sums that steer the iteration are accumulated in 2^-34 fixed point so the result does not depend
 // on atomic ordering.
+#include <cooperative_groups.h>
+
 #include "assoc.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace mht {
 
@@ -110,6 +114,7 @@ __global__ void assoc_init_kernel(ColView c, AssocWork w, int *tstart, int *tend
             *w.bb_nodes = 0ull;
             w.objective[0] = w.objective[1] = 0.0;
         }
+        if (i < n) w.freq[i] = 0;
         if (i < n) {  // tree column ranges
             const int t = c.tree[i];
             if (i == 0 || c.tree[i - 1] != t) tstart[t] = i;
@@ -202,7 +207,7 @@ __device__ __forceinline__ bool warp_run_min(int t, unsigned long long &key) {
 }
 
 template <bool FORCE>
-__global__ void __launch_bounds__(256) dual_rc_kernel(ColView c, AssocWork w) {
+__device__ __forceinline__ void dual_rc_body(ColView c, AssocWork w) {
     if (!FORCE && w.info[0]) return;
     const int n = *c.n_ptr;
     const int nround = (n + 31) & ~31;
@@ -228,9 +233,12 @@ __global__ void __launch_bounds__(256) dual_rc_kernel(ColView c, AssocWork w) {
         if (head && t >= 0) atomicMin(&w.tmin[t], key);
     }
 }
+template <bool FORCE>
+__global__ void __launch_bounds__(256) dual_rc_kernel(ColView c, AssocWork w) { dual_rc_body<FORCE>(c, w); }
+
 
 template <bool FORCE>
-__global__ void __launch_bounds__(256) dual_arg_kernel(ColView c, AssocWork w) {
+__device__ __forceinline__ void dual_arg_body(ColView c, AssocWork w) {
     if (!FORCE && w.info[0]) return;
     const int n = *c.n_ptr;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -240,6 +248,9 @@ __global__ void __launch_bounds__(256) dual_arg_kernel(ColView c, AssocWork w) {
         if (f64_key(w.rc[j]) == w.tmin[t]) atomicMax(&w.targ[t], j);
     }
 }
+template <bool FORCE>
+__global__ void __launch_bounds__(256) dual_arg_kernel(ColView c, AssocWork w) { dual_arg_body<FORCE>(c, w); }
+
 
 // subgradient, per-cluster Polyak step and bookkeeping, as four small grid kernels
 // (accumulators cl_m/cl_u/cl_cost/cl_nrm are zero on entry: assoc_init / du_apply leave them so)
@@ -247,13 +258,14 @@ __device__ __forceinline__ bool du_skip(const ColView &c, const AssocWork &w) {
     return w.info[0] || (c.idx && w.act_n[2]);
 }
 
-__global__ void du_trees_kernel(ColView c, AssocWork w) {
+__device__ __forceinline__ void du_trees_body(ColView c, AssocWork w) {
     if (du_skip(c, w)) return;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
         if (w.tstart[t] < 0) continue;
         const int cl = w.uf[t];
         if (w.cl_done[cl]) continue;
         const int j = w.targ[t];
+        w.freq[j] += 1;  // ergodic primal estimate: how often this column is the tree's Lagrangian choice
         atomicAdd((unsigned long long *)&w.cl_m[cl], (unsigned long long)to_fix(key_f64(w.tmin[t])));
         atomicAdd((unsigned long long *)&w.cl_cost[cl], (unsigned long long)to_fix(col_cost(c, j, t)));
         for (int k = 0; k < c.width; ++k) {
@@ -262,8 +274,10 @@ __global__ void du_trees_kernel(ColView c, AssocWork w) {
         }
     }
 }
+__global__ void du_trees_kernel(ColView c, AssocWork w) { du_trees_body(c, w); }
 
-__global__ void du_rows_kernel(ColView c, AssocWork w) {
+
+__device__ __forceinline__ void du_rows_body(ColView c, AssocWork w) {
     if (du_skip(c, w)) return;
     const int nr = *w.row_n;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += gridDim.x * blockDim.x) {
@@ -278,8 +292,10 @@ __global__ void du_rows_kernel(ColView c, AssocWork w) {
         if (ur > 0.0) atomicAdd((unsigned long long *)&w.cl_u[cl], (unsigned long long)to_fix(ur));
     }
 }
+__global__ void du_rows_kernel(ColView c, AssocWork w) { du_rows_body(c, w); }
 
-__global__ void du_decide_kernel(ColView c, AssocWork w) {
+
+__device__ __forceinline__ void du_decide_body(ColView c, AssocWork w) {
     if (du_skip(c, w)) return;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
         if (w.tstart[t] < 0 || w.uf[t] != t || w.cl_done[t]) continue;
@@ -315,8 +331,10 @@ __global__ void du_decide_kernel(ColView c, AssocWork w) {
         }
     }
 }
+__global__ void du_decide_kernel(ColView c, AssocWork w) { du_decide_body(c, w); }
 
-__global__ void du_apply_kernel(ColView c, AssocWork w) {
+
+__device__ __forceinline__ void du_apply_body(ColView c, AssocWork w) {
     if (du_skip(c, w)) {
         if (blockIdx.x == 0 && threadIdx.x == 0 && c.idx && w.act_n[2]) w.info[0] = 1;
         return;
@@ -340,9 +358,11 @@ __global__ void du_apply_kernel(ColView c, AssocWork w) {
         w.targ[t] = -1;
     }
 }
+__global__ void du_apply_kernel(ColView c, AssocWork w) { du_apply_body(c, w); }
+
 
 // runs after du_apply: clears the per-cluster accumulators/flags and advances the iteration state
-__global__ void du_finish_kernel(ColView c, AssocWork w) {
+__device__ __forceinline__ void du_finish_body(ColView c, AssocWork w) {
     if (w.info[0]) return;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
         w.cl_m[t] = 0;
@@ -360,6 +380,8 @@ __global__ void du_finish_kernel(ColView c, AssocWork w) {
         w.stall_ctr[2] = 0;
     }
 }
+__global__ void du_finish_kernel(ColView c, AssocWork w) { du_finish_body(c, w); }
+
 
 static void dual_update(const ColView &c, AssocWork &w, cudaStream_t s) {
     const int tb = (c.n_trees + 127) / 128;
@@ -374,7 +396,7 @@ static void dual_update(const ColView &c, AssocWork &w, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // primal greedy in parallel rounds
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024, 1) greedy_init_kernel(ColView c, AssocWork w, const int *tstart) {
+__device__ __forceinline__ void greedy_init_body(ColView c, AssocWork w, const int *tstart) {
     if (w.info[0]) return;
     __shared__ int left;
     if (threadIdx.x == 0) left = 0;
@@ -394,6 +416,17 @@ __global__ void __launch_bounds__(1024, 1) greedy_init_kernel(ColView c, AssocWo
     __syncthreads();
     if (threadIdx.x == 0) w.info[2] = left;
 }
+__global__ void __launch_bounds__(1024, 1) greedy_init_kernel(ColView c, AssocWork w, const int *tstart) { greedy_init_body(c, w, tstart); }
+
+
+// bidding key (lower wins): mode 0 = reduced cost; mode 1 = most frequent Lagrangian choice first
+// (rounding of the ergodic primal average), reduced cost as tie break
+__device__ __forceinline__ unsigned long long greedy_key(const AssocWork &w, int j) {
+    const unsigned long long k = f64_key(w.rc[j]);
+    if (w.stall_ctr[3] == 0) return k;
+    const unsigned long long f = (unsigned long long)(4095 - min(w.freq[j], 4095));
+    return (f << 52) | (k >> 12);
+}
 
 __device__ __forceinline__ bool rows_free(const ColView &c, const int *taken, int j) {
     for (int k = 0; k < c.width; ++k) {
@@ -403,7 +436,7 @@ __device__ __forceinline__ bool rows_free(const ColView &c, const int *taken, in
     return true;
 }
 
-__global__ void __launch_bounds__(256) greedy_prop_kernel(ColView c, AssocWork w) {
+__device__ __forceinline__ void greedy_prop_body(ColView c, AssocWork w) {
     if (w.info[0] || w.info[2] == 0) return;
     const int n = *c.n_ptr;
     const int nround = (n + 31) & ~31;
@@ -414,7 +447,7 @@ __global__ void __launch_bounds__(256) greedy_prop_kernel(ColView c, AssocWork w
             const int j = c.idx ? c.idx[i] : i;
             t = c.tree[j];
             if (!w.committed[t] && rows_free(c, w.row_taken, j))
-                key = f64_key(w.rc[j]);
+                key = greedy_key(w, j);
             else
                 t = -1;
         }
@@ -422,19 +455,23 @@ __global__ void __launch_bounds__(256) greedy_prop_kernel(ColView c, AssocWork w
         if (head && t >= 0) atomicMin(&w.prop_key[t], key);
     }
 }
+__global__ void __launch_bounds__(256) greedy_prop_kernel(ColView c, AssocWork w) { greedy_prop_body(c, w); }
 
-__global__ void __launch_bounds__(256) greedy_arg_kernel(ColView c, AssocWork w) {
+
+__device__ __forceinline__ void greedy_arg_body(ColView c, AssocWork w) {
     if (w.info[0] || w.info[2] == 0) return;
     const int n = *c.n_ptr;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int j = c.idx ? c.idx[i] : i;
         const int t = c.tree[j];
         if (w.committed[t]) continue;
-        if (f64_key(w.rc[j]) == w.prop_key[t] && rows_free(c, w.row_taken, j)) atomicMax(&w.prop_col[t], j);
+        if (greedy_key(w, j) == w.prop_key[t] && rows_free(c, w.row_taken, j)) atomicMax(&w.prop_col[t], j);
     }
 }
+__global__ void __launch_bounds__(256) greedy_arg_kernel(ColView c, AssocWork w) { greedy_arg_body(c, w); }
 
-__global__ void __launch_bounds__(1024, 1) greedy_commit_kernel(ColView c, AssocWork w) {
+
+__device__ __forceinline__ void greedy_commit_body(ColView c, AssocWork w) {
     if (w.info[0] || w.info[2] == 0) return;
     const int T = c.n_trees, R = c.n_rows;
     __shared__ int left;
@@ -478,9 +515,11 @@ __global__ void __launch_bounds__(1024, 1) greedy_commit_kernel(ColView c, Assoc
     for (int r = threadIdx.x; r < R; r += blockDim.x) w.row_bid[r] = kKeyInf;
     if (threadIdx.x == 0) w.info[2] = left;
 }
+__global__ void __launch_bounds__(1024, 1) greedy_commit_kernel(ColView c, AssocWork w) { greedy_commit_body(c, w); }
+
 
 // adopt the greedy solution for every cluster it improves
-__global__ void __launch_bounds__(1024, 1) greedy_finish_kernel(ColView c, AssocWork w, const int *tstart) {
+__device__ __forceinline__ void greedy_finish_body(ColView c, AssocWork w, const int *tstart) {
     if (w.info[0] || w.info[2] != 0) return;
     const int T = c.n_trees;
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
@@ -512,6 +551,54 @@ __global__ void __launch_bounds__(1024, 1) greedy_finish_kernel(ColView c, Assoc
     for (int t = threadIdx.x; t < T; t += blockDim.x) {  // leave the dual-update accumulators clean
         w.cl_cost[t] = 0;
         w.cl_flag[t] = 0;
+    }
+}
+__global__ void __launch_bounds__(1024, 1) greedy_finish_kernel(ColView c, AssocWork w, const int *tstart) { greedy_finish_body(c, w, tstart); }
+
+
+// ------------------------------------------------------------------------------------------------
+// The whole dual loop as ONE persistent cooperative kernel (grid = resident CTAs, grid.sync between
+// phases): `iters` subgradient iterations, a greedy primal pass every kGreedyEvery iterations whose
+// bidding rounds stop as soon as every tree is committed.  Replaces ~7 launches per iteration.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dual_loop_persistent_kernel(ColView c, AssocWork w, int iters) {
+    cg::grid_group grid = cg::this_grid();
+    for (int it = 0; it < iters; ++it) {
+        if (((volatile int *)w.info)[0]) break;  // uniform: written before the last grid.sync
+        if (it % kGreedyEvery == 0) {
+            dual_rc_body<false>(c, w);
+            grid.sync();
+            for (int mode = 0; mode < (it ? 2 : 1); ++mode) {
+                if (blockIdx.x == 0 && threadIdx.x == 0) w.stall_ctr[3] = mode;
+                if (blockIdx.x == 0) greedy_init_body(c, w, w.tstart);
+                grid.sync();
+                for (int r = 0; r < kGreedyRounds; ++r) {
+                    if (((volatile int *)w.info)[2] == 0) break;
+                    greedy_prop_body(c, w);
+                    grid.sync();
+                    greedy_arg_body(c, w);
+                    grid.sync();
+                    if (blockIdx.x == 0) greedy_commit_body(c, w);
+                    grid.sync();
+                }
+                if (blockIdx.x == 0) greedy_finish_body(c, w, w.tstart);
+                grid.sync();
+            }
+        }
+        dual_rc_body<false>(c, w);
+        grid.sync();
+        dual_arg_body<false>(c, w);
+        grid.sync();
+        du_trees_body(c, w);
+        grid.sync();
+        du_rows_body(c, w);
+        grid.sync();
+        du_decide_body(c, w);
+        grid.sync();
+        du_apply_body(c, w);
+        grid.sync();
+        du_finish_body(c, w);
+        grid.sync();
     }
 }
 
@@ -624,7 +711,10 @@ __global__ void __launch_bounds__(256) active_scatter_kernel(ColView c, AssocWor
         __syncthreads();
         int before = __popc(b & ((1u << lane) - 1));
         for (int k = 0; k < wid; ++k) before += wsum[k];
-        if (f) w.act_col[w.act_tile[q * plane + tile] + before] = j;
+        if (f) {
+            w.act_col[w.act_tile[q * plane + tile] + before] = j;
+            w.freq[j] = 0;
+        }
         __syncthreads();
     }
 }
@@ -990,6 +1080,7 @@ __global__ void __launch_bounds__(1024, 1) final_objective_kernel(ColView c, Ass
     __syncthreads();
     if (threadIdx.x == 0) {
         w.objective[1] = from_fix(ob);
+        w.info[12] = w.act_n[0];
         w.info[10] = (w.info[5] == 0 && w.info[6] == 0 && w.info[11] == 0) ? 1 : 0;  // certified
     }
 }
@@ -1013,6 +1104,7 @@ static int64_t carve_all(Carver &cv, int64_t cap_cols, int64_t T, int64_t R, int
                          int **tstart, int **tend, double **fscratch) {
     AssocWork d;
     d.rc = cv.take<double>(cap_cols);
+    d.freq = cv.take<int>(cap_cols);
     d.tmin = cv.take<unsigned long long>(T);
     d.targ = cv.take<int>(T);
     d.uf = cv.take<int>(T);
@@ -1110,16 +1202,28 @@ static void greedy_pass(const ColView &c, AssocWork &w, int grid_dim, cudaStream
     greedy_finish_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
 }
 
-static void dual_loop(const ColView &c, AssocWork &w, int iters, int grid_dim, cudaStream_t s) {
-    for (int it = 0; it < iters; ++it) {
-        if (it % kGreedyEvery == 0) {
-            dual_rc_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);  // rc at the current multipliers
-            greedy_pass(c, w, grid_dim, s);
-        }
-        dual_rc_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
-        dual_arg_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
-        dual_update(c, w, s);
+static int persistent_grid() {
+    static int blocks = 0;
+    if (!blocks) {
+        int per_sm = 0, dev = 0, sms = kSMs;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dual_loop_persistent_kernel, 256, 0);
+        if (per_sm > 4) per_sm = 4;
+        blocks = per_sm > 0 ? per_sm * sms : sms;
     }
+    return blocks;
+}
+
+static int dual_loop(const ColView &c, AssocWork &w, int iters, int grid_dim, cudaStream_t s) {
+    ColView cc = c;
+    AssocWork ww = w;
+    void *args[] = {&cc, &ww, &iters};
+    // grid.sync cost grows with the grid: the active list (~1e5 columns) gets one CTA per SM
+    const int grid = grid_dim < persistent_grid() ? grid_dim : persistent_grid();
+    MHT_CUDA(cudaLaunchCooperativeKernel((void *)dual_loop_persistent_kernel, dim3(grid), dim3(256), args,
+                                         0, s));
+    return MHT_OK;
 }
 
 int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, int grid_dim, cudaStream_t s,
@@ -1131,13 +1235,13 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
     dual_arg_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
     dual_update(c, w, s);
     if (!sift) {
-        dual_loop(c, w, max_iters, grid_dim, s);
+        if (int rc = dual_loop(c, w, max_iters, grid_dim, s)) return rc;
     } else {
         // sifting: price all columns, iterate on the active list, re-price; kSiftRounds times
         ColView a = c;
         a.idx = w.act_col;
         a.n_ptr = w.act_n;
-        const int act_grid = grid_dim < kSMs * 2 ? grid_dim : kSMs * 2;
+        const int act_grid = kSMs;
         for (int round = 0; round < kSiftRounds; ++round) {
             if (round) sift_rearm_kernel<<<1, 1024, 0, s>>>(c, w);
             dual_rc_kernel<true><<<grid_dim, 256, 0, s>>>(c, w);
@@ -1145,7 +1249,7 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
             active_scan_kernel<<<1, 1024, 0, s>>>(c, w);
             active_scatter_kernel<<<grid_dim, 256, 0, s>>>(c, w);
             reset_tree_min_kernel<<<(c.n_trees + 255) / 256, 256, 0, s>>>(c.n_trees, w);
-            dual_loop(a, w, max_iters, act_grid, s);
+            if (int rc = dual_loop(a, w, max_iters, act_grid, s)) return rc;
         }
     }
     MHT_CUDA(cudaGetLastError());

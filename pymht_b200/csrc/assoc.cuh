@@ -24,6 +24,7 @@ struct ColView {
 struct AssocWork {
     // per column
     double *rc;                // [cap_cols]
+    int *freq;                 // [cap_cols] how often the column was its tree's argmin (primal rounding)
     // per tree
     unsigned long long *tmin;  // ordered key of min reduced cost
     int *targ;                 // argmin column (ties -> last)
