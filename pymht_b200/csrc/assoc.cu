@@ -51,34 +51,13 @@ __device__ __forceinline__ double col_cost(const ColView &c, int j, int t) {
 // ------------------------------------------------------------------------------------------------
 // union-find (link the larger root under the smaller: label = smallest tree index)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int uf_find(int *uf, int x) {
-    int p = ((volatile int *)uf)[x];
-    while (p != x) {
-        const int gp = ((volatile int *)uf)[p];
-        if (gp != p) uf[x] = gp;  // path halving (benign race)
-        x = p;
-        p = gp;
-    }
-    return x;
-}
-__device__ __forceinline__ void uf_union(int *uf, int a, int b) {
-    while (true) {
-        a = uf_find(uf, a);
-        b = uf_find(uf, b);
-        if (a == b) return;
-        if (a > b) {
-            const int t = a;
-            a = b;
-            b = t;
-        }
-        if (atomicCAS(&uf[b], b, a) == b) return;
-    }
-}
-
 __global__ void assoc_init_kernel(ColView c, AssocWork w, int *tstart, int *tend, int warm) {
     const int T = c.n_trees, R = c.n_rows;
-    const int n = *c.n_ptr;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max(max(T + 1, R), n); i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max(T + 1, R); i += gridDim.x * blockDim.x) {
+        if (i < T) {
+            tstart[i] = -1;
+            tend[i] = -1;
+        }
         if (i < T) {
             w.uf[i] = i;
             w.tmin[i] = kKeyInf;
@@ -114,19 +93,17 @@ __global__ void assoc_init_kernel(ColView c, AssocWork w, int *tstart, int *tend
             *w.bb_nodes = 0ull;
             w.objective[0] = w.objective[1] = 0.0;
         }
-        if (i < n) w.freq[i] = 0;
-        if (i < n) {  // tree column ranges
-            const int t = c.tree[i];
-            if (i == 0 || c.tree[i - 1] != t) tstart[t] = i;
-            if (i == n - 1 || c.tree[i + 1] != t) tend[t] = i + 1;
-        }
     }
 }
 
-__global__ void assoc_clear_ranges_kernel(int T, int *tstart, int *tend) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x) {
-        tstart[i] = -1;
-        tend[i] = -1;
+// per-column part of the reset: tree column ranges, argmin frequencies
+__global__ void assoc_init_cols_kernel(ColView c, AssocWork w, int *tstart, int *tend) {
+    const int n = *c.n_ptr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        w.freq[i] = 0;
+        const int t = c.tree[i];
+        if (i == 0 || c.tree[i - 1] != t) tstart[t] = i;
+        if (i == n - 1 || c.tree[i + 1] != t) tend[t] = i + 1;
     }
 }
 
@@ -134,20 +111,17 @@ __global__ void uf_union_cols_kernel(ColView c, int *uf, int *row_owner, int *ro
     const int n = *c.n_ptr;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         const int t = c.tree[j];
+        // forest columns: siblings share every plane but the newest, so only the first sibling (the
+        // miss child) handles the inherited planes and everybody handles the newest one
+        const bool inherited = !c.meas || c.meas[j] == 0;
         for (int k = 0; k < c.width; ++k) {
+            if (!inherited && k != c.plane_new) continue;
             const int r = c.rows[(long long)k * c.stride + j];
             if (r < 0) continue;
-            // siblings share every plane but the newest: the left neighbour already did this row
-            if ((threadIdx.x & 31) && c.rows[(long long)k * c.stride + j - 1] == r && c.tree[j - 1] == t) continue;
-            int o = row_owner[r];
-            if (o < 0) {
-                o = atomicCAS(&row_owner[r], -1, t);
-                if (o < 0) o = t;
-            }
-            if (o != t) {
-                row_multi[r] = 1;
-                uf_union(uf, t, o);
-            }
+            // generic columns: the left neighbour (same tree, same row) already did this row
+            if (!c.meas && (threadIdx.x & 31) && c.rows[(long long)k * c.stride + j - 1] == r && c.tree[j - 1] == t)
+                continue;
+            uf_touch_row(uf, row_owner, row_multi, r, t);
         }
     }
 }
@@ -1175,11 +1149,21 @@ void assoc_carve(void *d_work, int64_t cap_cols, int64_t T, int64_t R, int64_t c
     carve_all(cv, cap_cols, T, R, cap_cand, w, &g_tstart, &g_tend, &g_fscratch);
 }
 
-static int cluster_phase(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s, bool warm = false) {
+int assoc_begin(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s, bool warm) {
+    (void)grid_dim;
+    const int n = (c.n_trees + 1 > c.n_rows ? c.n_trees + 1 : c.n_rows);
+    assoc_init_kernel<<<(n + 255) / 256, 256, 0, s>>>(c, w, w.tstart, g_tend, warm ? 1 : 0);
+    MHT_CUDA(cudaGetLastError());
+    return MHT_OK;
+}
+
+static int cluster_phase(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s, bool warm = false,
+                         bool pre_unioned = false) {
     const int T = c.n_trees;
-    assoc_clear_ranges_kernel<<<(T + 255) / 256, 256, 0, s>>>(T, g_tstart, g_tend);
-    assoc_init_kernel<<<grid_dim, 256, 0, s>>>(c, w, g_tstart, g_tend, warm ? 1 : 0);
-    uf_union_cols_kernel<<<grid_dim, 256, 0, s>>>(c, w.uf, w.row_owner, w.row_mark);
+    if (!pre_unioned)
+        if (int rc = assoc_begin(c, w, grid_dim, s, warm)) return rc;
+    assoc_init_cols_kernel<<<grid_dim, 256, 0, s>>>(c, w, g_tstart, g_tend);
+    if (!pre_unioned) uf_union_cols_kernel<<<grid_dim, 256, 0, s>>>(c, w.uf, w.row_owner, w.row_mark);
     if (warm) warm_fix_kernel<<<(c.n_rows + 255) / 256, 256, 0, s>>>(c.n_rows, w.row_mark, w.u, w.best_u);
     uf_flatten_kernel<<<(T + 255) / 256, 256, 0, s>>>(T, w.uf);
     row_list_kernel<<<(c.n_rows + 255) / 256, 256, 0, s>>>(c.n_rows, w.row_owner, w.row_list, w.row_n);
@@ -1227,8 +1211,8 @@ static int dual_loop(const ColView &c, AssocWork &w, int iters, int grid_dim, cu
 }
 
 int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, int grid_dim, cudaStream_t s,
-                cudaEvent_t after_cluster, bool warm_start, bool sift) {
-    if (int rc = cluster_phase(c, w, grid_dim, s, warm_start)) return rc;
+                cudaEvent_t after_cluster, bool warm_start, bool sift, bool pre_unioned) {
+    if (int rc = cluster_phase(c, w, grid_dim, s, warm_start, pre_unioned)) return rc;
     if (after_cluster) MHT_CUDA(cudaEventRecord(after_cluster, s));
     // iteration 0 settles every conflict-free cluster (all singletons) exactly
     dual_rc_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
@@ -1293,6 +1277,8 @@ static int make_view(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t wi
     assoc_carve((char *)d_work + 256, n_cols, n_trees, n_rows, n_cols, w);
     c->n_ptr = n_dev;
     c->idx = nullptr;
+    c->meas = nullptr;
+    c->plane_new = -1;
     c->cost = d_cost;
     c->tree_base = nullptr;
     c->tree = d_tree;

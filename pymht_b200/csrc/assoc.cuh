@@ -15,6 +15,9 @@ struct ColView {
     const double *tree_base;   // [T] or null: cost_j := cost[j] - tree_base[tree[j]]
     const int *tree;           // [n] non-decreasing
     const int *rows;           // [width][stride]  row id or <0
+    const int *meas;           // null, or measurementNumber per column: 0 marks the first of a sibling run
+                               // whose columns share every row plane except plane_new
+    int plane_new;
     long long stride;
     int width;
     int n_trees;
@@ -67,12 +70,53 @@ struct AssocWork {
     double *objective;         // [2]: lower bound, objective
 };
 
+// ---- lock-free union-find shared with the forest's emit kernel (label = smallest tree index) ----
+__device__ __forceinline__ int uf_find(int *uf, int x) {
+    int p = ((volatile int *)uf)[x];
+    while (p != x) {
+        const int gp = ((volatile int *)uf)[p];
+        if (gp != p) uf[x] = gp;  // path halving (benign race)
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+__device__ __forceinline__ void uf_union(int *uf, int a, int b) {
+    while (true) {
+        a = uf_find(uf, a);
+        b = uf_find(uf, b);
+        if (a == b) return;
+        if (a > b) {
+            const int t = a;
+            a = b;
+            b = t;
+        }
+        if (atomicCAS(&uf[b], b, a) == b) return;
+    }
+}
+// tree t uses measurement row r: first toucher owns the row, later trees are united with the owner
+__device__ __forceinline__ void uf_touch_row(int *uf, int *row_owner, int *row_multi, int r, int t) {
+    int o = row_owner[r];
+    if (o < 0) {
+        o = atomicCAS(&row_owner[r], -1, t);
+        if (o < 0) o = t;
+    }
+    if (o != t) {
+        row_multi[r] = 1;
+        uf_union(uf, t, o);
+    }
+}
+
 int64_t assoc_workspace_bytes(int64_t cap_cols, int64_t n_trees, int64_t n_rows, int64_t cap_cand);
 void assoc_carve(void *d_work, int64_t cap_cols, int64_t n_trees, int64_t n_rows, int64_t cap_cand, AssocWork *w);
+// per-solve reset of the tree / row state (everything that does not need the column count); a caller that
+// unites trees itself (forest emit kernel) calls this first and passes pre_unioned = true to assoc_solve
+int assoc_begin(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s, bool warm_start);
 // cluster labels only (uf[t] = smallest tree index of the component); async
 int assoc_cluster(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s);
 // full solve; async; results in w.sel / w.info / w.objective
 int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, int grid_dim, cudaStream_t s,
-                cudaEvent_t after_cluster = nullptr, bool warm_start = false, bool sift = false);
+                cudaEvent_t after_cluster = nullptr, bool warm_start = false, bool sift = false,
+                bool pre_unioned = false);
 
 }  // namespace mht

@@ -118,6 +118,7 @@ struct ScanArgs {
     unsigned char *used;
     ScanStatus *status;
     long long cap_nodes, cap_par;
+    int *uf, *row_owner, *row_multi;   // association union-find state (clusters are built while emitting)
 };
 
 // exclusive scan of live range lengths over tree slots (single CTA; T <= ~10^5)
@@ -328,8 +329,12 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, int *scr
             for (int w = 0; w < a.W; ++w) {
                 const int back = ((a.scan - w) % a.W + a.W) % a.W;  // scans since plane w was written
                 const int s_w = a.scan - back;
-                s_path[w * kTile + tid] =
+                const int r =
                     (w != plane_cur && s_w > root_scan) ? a.rows_prev[(long long)w * a.stride + pos] : -1;
+                s_path[w * kTile + tid] = r;
+                // cluster step (tracker.py:961-974): every measurement on the path links this tree to
+                // the other trees using it; all children inherit these rows
+                if (r >= 0) uf_touch_row(a.uf, a.row_owner, a.row_multi, r, t);
             }
             int k = 0;
             int *dst = scratch + tile_base + loc + 1;
@@ -376,6 +381,7 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, int *scr
                 xo3 = s_d[3 * kTile + p] + fma((double)s_K[7 * kTile + p], v1, (double)s_K[6 * kTile + p] * v0);
                 cn = s_d[12 * kTile + p] + (0.5 * d2 + s_d[10 * kTile + p]);
                 a.used[m] = 1;
+                uf_touch_row(a.uf, a.row_owner, a.row_multi, row_new, t);
             }
             a.cur.xa[g] = make_double2(xo0, xo1);
             a.cur.xb[g] = make_double2(xo2, xo3);
@@ -702,23 +708,17 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     a.status = f->status_d;
     a.cap_nodes = f->cap_nodes;
     a.cap_par = f->cap_par;
+    a.uf = f->aw.uf;
+    a.row_owner = f->aw.row_owner;
+    a.row_multi = f->aw.row_mark;
 
     const int grid_dim = kSMs * 8;
     MHT_CUDA(cudaEventRecord(f->ev[0], s));
-    MHT_CUDA(cudaMemsetAsync(f->used_d, 0, (size_t)(M ? M : 1), s));
-    live_scan_kernel<<<1, 1024, 0, s>>>(a);
-    if (int rc = launch_grid_build(d_z, (int)M, grid, cell_start, cell_fill, gz, gidx, s)) return rc;
-    forest_count_kernel<<<grid_dim, kTile, 0, s>>>(a);
-    forest_scan_tiles_kernel<<<1, 1024, 0, s>>>(a);
-    forest_emit_kernel<<<grid_dim, kTile, emit_smem_bytes(f->W), s>>>(a, (int *)f->aw.rc);
-    tree_off_kernel<<<(f->T + 256) / 256, 256, 0, s>>>(a);
-    MHT_CUDA(cudaGetLastError());
-    MHT_CUDA(cudaEventRecord(f->ev[1], s));
-
-    f->scan = k;
     ColView c;
     c.n_ptr = f->d_nc;
     c.idx = nullptr;
+    c.meas = a.cur.meas;
+    c.plane_new = k % f->W;
     c.cost = a.cur.cnllr;
     c.tree_base = f->ts.root_cnllr;
     c.tree = a.cur.tree;
@@ -732,9 +732,21 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     // warm start: measurement rows keep their ids for W scans, so last scan's multipliers are a good
     // starting point; the plane being recycled for this scan starts from zero
     MHT_CUDA(cudaMemsetAsync(f->aw.u + (size_t)(k % f->W) * f->cfg.max_meas, 0, sizeof(double) * f->cfg.max_meas, s));
+    if (int rc = assoc_begin(c, f->aw, grid_dim, s, k > 1)) return rc;
+    MHT_CUDA(cudaMemsetAsync(f->used_d, 0, (size_t)(M ? M : 1), s));
+    live_scan_kernel<<<1, 1024, 0, s>>>(a);
+    if (int rc = launch_grid_build(d_z, (int)M, grid, cell_start, cell_fill, gz, gidx, s)) return rc;
+    forest_count_kernel<<<grid_dim, kTile, 0, s>>>(a);
+    forest_scan_tiles_kernel<<<1, 1024, 0, s>>>(a);
+    forest_emit_kernel<<<grid_dim, kTile, emit_smem_bytes(f->W), s>>>(a, (int *)f->aw.rc);
+    tree_off_kernel<<<(f->T + 256) / 256, 256, 0, s>>>(a);
+    MHT_CUDA(cudaGetLastError());
+    MHT_CUDA(cudaEventRecord(f->ev[1], s));
+
+    f->scan = k;
     static const long long sift_min = getenv("MHT_SIFT_MIN") ? atoll(getenv("MHT_SIFT_MIN")) : 1000000;
     const bool sift = f->h_level_nodes > sift_min;  // last scan's hypothesis count is the size hint
-    if (int rc = assoc_solve(c, f->aw, f->cfg.max_dual_iters, 400000, kSMs * 8, s, f->ev[5], f->scan > 1, sift))
+    if (int rc = assoc_solve(c, f->aw, f->cfg.max_dual_iters, 400000, kSMs * 8, s, f->ev[5], f->scan > 1, sift, true))
         return rc;
     MHT_CUDA(cudaEventRecord(f->ev[2], s));
 
