@@ -245,13 +245,7 @@ def main():
     t_dev = sum(d["ms_total"] for d in timed) * 1e-3
     t_e2e = sum(e2e_times)
     if dist is not None:
-        t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e = t.tolist()
-        # the one exchange of the sharded forest: every rank gets every sector's track count
-        summary = torch.tensor([n_tracks], dtype=torch.int64, device="cuda")
-        gathered = [torch.zeros_like(summary) for _ in range(world)]
-        dist.all_gather(gathered, summary)
+        t_dev, t_e2e, sector_tracks = exchange(dist, torch.device("cuda", local_rank), t_dev, t_e2e, n_tracks)
     if rank == 0:
         K = len(timed)
         value = world * K / t_dev
@@ -298,15 +292,27 @@ def main():
         dist.destroy_process_group()
 
 
+def exchange(dist, device, t_dev, t_e2e, n_tracks):
+    """Multi-rank reduction of one bench run: device/e2e times -> MAX over ranks (a step is as slow as
+    the slowest sector), and the only exchange the sector-sharded forest needs: every rank learns every
+    sector's live-track count (all_gather).  Backend-agnostic (NCCL on GPUs, gloo in the CPU test)."""
+    import torch
+    t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    summary = torch.tensor([n_tracks], dtype=torch.int64, device=device)
+    gathered = [torch.zeros_like(summary) for _ in range(dist.get_world_size())]
+    dist.all_gather(gathered, summary)
+    return float(t[0]), float(t[1]), [int(g[0]) for g in gathered]
+
+
 def launches_per_scan(d):
     """Kernel launches of libmht_b200 per scan, counted from the launch sequence in csrc/forest.cu and
-    csrc/assoc.cu (gate 6, cluster 7, settle pass 7, per dual iteration 7, per greedy pass 123, sifting
-    round 6, final 11, track update 1)."""
-    iters = int(os.environ.get("MHT_DUAL_ITERS", "120"))
-    greedy = (iters + 39) // 40
-    loop = iters * 7 + greedy * (1 + 1 + 3 * 40 + 1)
+    csrc/assoc.cu: gate 6 (live_scan, grid_build, count, scan_tiles, emit, tree_off) + assoc reset 1 +
+    cluster bookkeeping 5 + settle pass 7 + dual loop (ONE persistent cooperative kernel per round; with
+    sifting 3 rounds, each preceded by a pricing pass, 3 active-list kernels and a reset, plus 2 re-arms)
+    + final bound/candidates/repair 11 + track update 1."""
     sift = d["n_children"] > 1000000
-    return 6 + 7 + 7 + (3 * (6 + loop) if sift else loop) + 11 + 1
+    return 6 + 1 + 5 + 7 + (3 * 6 + 2 if sift else 1) + 11 + 1
 
 
 if __name__ == "__main__":

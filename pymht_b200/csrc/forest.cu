@@ -673,6 +673,15 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     }
     cudaStream_t s = f->stream;
     const int k = f->scan + 1;
+    if (f->T == 0) {  // no trees yet: the scan only advances the clock (tracker.py:207 loops over nothing)
+        f->scan = k;
+        f->h_level_nodes = 0;
+        f->h_level_ptab = 0;
+        f->last_tracks.clear();
+        if (info) memset(info, 0, sizeof(*info));
+        if (h_used && M) memset(h_used, 0, (size_t)M);
+        return MHT_OK;
+    }
     ScanArgs a;
     a.model = f->cfg.model;
     a.prev = f->lv[f->scan % f->nslots];

@@ -243,8 +243,12 @@ class Tracker:
             meas, x, cn, P = self._history(slot)
             root = self._slot_info[slot]
             first_scan = root.scanNumber
+            # current root of the tree: N scans above the leaf once the window is full (tracker.py:1219-1231);
+            # a track terminated this scan was not pruned, its root is one scan older
+            pruned_at = leaf.scanNumber - (0 if leaf.status == STATUS_TAGS[0] else 1)
+            root_scan = max(first_scan, pruned_at - self.N)
             chain = Target(root.time, first_scan, x[0].copy(), P[0].copy(), ID=root.ID, P_d=root.P_d,
-                           status=root.status, cumulativeNLLR=float(cn[0]))
+                           status=root.status, cumulativeNLLR=float(cn[0]), isRoot=(root_scan == first_scan))
             for k in range(1, len(meas) - 1):
                 sc = first_scan + k
                 scan = self.__scanHistory__[sc - 1]
@@ -252,7 +256,7 @@ class Tracker:
                 chain = Target(scan.time, sc, x[k].copy(), P[k].copy(), ID=root.ID, P_d=root.P_d, parent=chain,
                                measurementNumber=m,
                                measurement=(np.asarray(scan.measurements)[m - 1] if m > 0 else None),
-                               cumulativeNLLR=float(cn[k]))
+                               cumulativeNLLR=float(cn[k]), isRoot=(sc == root_scan))
             assert first_scan + len(meas) - 1 == leaf.scanNumber
             leaf._parent = chain
         return load

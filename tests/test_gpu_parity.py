@@ -239,3 +239,89 @@ def test_large_random_forest_properties():
         assert len(nodes) + info["n_dead"] == info["n_trees"]
         assert info["n_children"] == info["n_parents"] + info["n_pairs"]
     trk.close()
+
+
+def _small_tracker(**kw):
+    from pymht_b200.tracker import Tracker
+    from pymht_b200.models import pv
+    args = dict(N=3, P_d=0.9, maxTargets=8, maxNodes=1 << 12, maxParents=1 << 10, maxMeasurements=256)
+    args.update(kw)
+    trk = Tracker(pv, 2.5, 1e-4, 1e-9, **args)
+    trk.mergeThreshold = 0.0
+    return trk, pv
+
+
+def test_edge_cases_empty_scan_no_targets_and_parent_chain():
+    """Edge cases the reference handles: a scan before any target exists, an empty scan (all tracks
+    coast on the miss hypothesis), and Target.parent chains that reproduce the history."""
+    from pymht_b200.pyTarget import Target
+    from pymht_b200.utils.classDefinitions import MeasurementList
+    from pymht_b200.tracker import backtrackMeasurementNumbers
+    trk, pv = _small_tracker()
+    trk.addMeasurementList(MeasurementList(1.0, np.zeros((3, 2), dtype=np.float32)))   # no targets yet
+    assert len(trk.getTrackNodes()) == 0
+    x0 = np.array([10.0, 20.0, 1.0, -1.0])
+    trk.initiateTarget(Target(1.0, None, x0, pv.P0))
+    assert trk.getTrackNodes()[0].scanNumber == 1 and trk.getTrackNodes()[0].isRoot
+    trk.addMeasurementList(MeasurementList(3.5, np.zeros((0, 2), dtype=np.float32)))   # empty scan
+    node = trk.getTrackNodes()[0]
+    assert node.measurementNumber == 0 and node.scanNumber == 2
+    A = pv.Phi(2.5).astype(float)
+    np.testing.assert_allclose(node.x_0, A @ x0, rtol=1e-12)
+    assert node.cumulativeNLLR == pytest.approx(-np.log(1 - 0.9), rel=1e-12)
+    z = np.array([[15.2, 15.1], [400.0, 400.0]], dtype=np.float32)
+    trk.addMeasurementList(MeasurementList(6.0, z))
+    node = trk.getTrackNodes()[0]
+    assert node.measurementNumber == 1 and np.allclose(node.measurement, z[0])
+    # parent chain: leaf -> miss node -> initial node, consistent with backtrackMeasurementNumbers
+    assert backtrackMeasurementNumbers([node]) == [[0, 1]]
+    assert node.parent.measurementNumber == 0 and node.parent.scanNumber == 2
+    assert node.parent.parent.parent is None and node.parent.parent.scanNumber == 1
+    np.testing.assert_allclose(node.parent.parent.x_0, x0)
+    assert node.getScore() == pytest.approx(node.cumulativeNLLR)
+    trk.close()
+
+
+def test_capacity_errors_are_loud_and_leave_the_forest_usable():
+    from pymht_b200.pyTarget import Target
+    from pymht_b200.utils.classDefinitions import MeasurementList
+    trk, pv = _small_tracker(maxNodes=16, maxParents=16, maxMeasurements=64)
+    trk.initiateTarget(Target(0.0, None, np.array([0.0, 0.0, 0.0, 0.0]), pv.P0))
+    with pytest.raises(_lib.MhtError) as e:      # more measurements than max_meas
+        trk.addMeasurementList(MeasurementList(2.5, np.zeros((65, 2), dtype=np.float32)))
+    assert e.value.code == _lib.MHT_E_CAPACITY
+    trk.__scanHistory__.pop()
+    z = np.random.RandomState(0).normal(scale=1.0, size=(40, 2)).astype(np.float32)   # 41 children > 16 nodes
+    with pytest.raises(_lib.MhtError) as e:
+        trk.addMeasurementList(MeasurementList(2.5, z))
+    assert e.value.code == _lib.MHT_E_CAPACITY and "capacity" in str(e.value)
+    trk.__scanHistory__.pop()
+    trk.addMeasurementList(MeasurementList(2.5, z[:5]))   # still usable afterwards
+    assert len(trk.getTrackNodes()) == 1 and trk.scanInfo[-1]["n_children"] == 6
+    trk.close()
+
+
+def test_initiate_target_respects_merge_threshold():
+    """Tracker.initiateTarget drops a new target closer than mergeThreshold to any live leaf
+    (reference tracker.py:147-160 / pyTarget.py:181-189)."""
+    from pymht_b200.pyTarget import Target
+    trk, pv = _small_tracker()
+    trk.mergeThreshold = 25.0
+    trk.initiateTarget(Target(0.0, None, np.array([0.0, 0.0, 1.0, 0.0]), pv.P0))
+    trk.initiateTarget(Target(0.0, None, np.array([10.0, 0.0, 1.0, 0.0]), pv.P0))    # 10 m away: dropped
+    trk.initiateTarget(Target(0.0, None, np.array([100.0, 0.0, 1.0, 0.0]), pv.P0))   # kept
+    assert [n.ID for n in trk.getTrackNodes()] == [0, 1]
+    assert [float(n.x_0[0]) for n in trk.getTrackNodes()] == [0.0, 100.0]
+    trk.close()
+
+
+def test_determinism_same_inputs_same_outputs():
+    """Two runs of the same scenario give bit-identical selections and scores (fixed-point sums in the
+    dual iteration make the result independent of atomic ordering)."""
+    runs = []
+    for _ in range(2):
+        out = []
+        for k, g, pre, trk, nodes, hist, info in _replay_tracker("cfg5_small"):
+            out.append((hist, [n.cumulativeNLLR for n in nodes], info["objective"], info["lower_bound"]))
+        runs.append(out)
+    assert runs[0] == runs[1]
