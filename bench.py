@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (targets, radarRange, lambda_phi, N, P_d, seed, maxNodes, maxParents)
-    "cfg3_1k_targets_5k_meas_N6": (1000, 1142.0, 1e-3, 6, 0.9, 1234, 96 << 20, 24 << 20),
+    "cfg3_1k_targets_5k_meas_N6": (1000, 1142.0, 1e-3, 6, 0.9, 1234, 144 << 20, 32 << 20),
     "cfg2_100_targets_1k_meas_N4": (100, 1702.0, 1e-4, 4, 0.9, 1234, 1 << 22, 1 << 20),
 }
 T_RADAR = 2.5
@@ -275,7 +275,7 @@ def main():
             "stage_ms": {k: float(np.mean([d[k] for d in timed])) for k in
                          ("ms_gate", "ms_cluster", "ms_assoc", "ms_prune", "ms_total")},
             "scan_stats": {k: float(np.mean([d[k] for d in timed])) for k in
-                           ("n_parents", "n_children", "n_pairs", "n_clusters", "n_multi_clusters", "dual_iters",
+                           ("n_trees", "n_parents", "n_children", "n_pairs", "n_clusters", "n_multi_clusters", "dual_iters",
                             "n_candidates", "bb_nodes", "certified", "lower_bound", "objective", "n_active")},
             "forest_hbm_bytes": dev_bytes,
         }
