@@ -76,7 +76,9 @@ class Tracker:
         self._lib = _lib.load()
         self._forest = None
         self._slots = []                    # forest slot of each live track (list order = reference order)
-        self._slot_info = {}                # slot -> dict(ID, time0, x0, P0, P_d)
+        self._slot_info = {}                # slot -> initial Target of the track
+        self._last = None                   # per-track arrays of the last scan
+        self._live_rows = None
         self._create_forest()
 
     # ------------------------------------------------------------------------------------------
@@ -132,10 +134,11 @@ class Tracker:
         node = Target(newTarget.time, len(self.__scanHistory__), x0.copy(), P0.copy(), ID=self.trackIdCounter,
                       P_d=self.default_P_d, status=newTarget.status, isRoot=True)
         self.trackIdCounter += 1
+        current = self.getTrackNodes()
         self._slots.append(slot.value)
         self._slot_info[slot.value] = node
         self.__targetList__.append(node)
-        self.__trackNodes__ = np.append(self.__trackNodes__, node)
+        self.__trackNodes__ = np.append(current, node)
         self.__targetWindowSize__.append(self.N)
 
     # ------------------------------------------------------------------------------------------
@@ -181,7 +184,11 @@ class Tracker:
             print(self.getTimeLogString())
 
     def _collect_tracks(self, scanList):
-        """Selected hypothesis per track (tracker.py:228-236), termination (tracker.py:252-253)."""
+        """Selected hypothesis per track (tracker.py:228-236), termination (tracker.py:252-253).
+
+        The per-track arrays are read back every scan; the `Target` objects for live tracks are built
+        lazily by getTrackNodes() (terminated tracks are materialised at once, history included, because
+        their window nodes leave the device store)."""
         cap = max(len(self._slots), 1)
         n = C.c_int32()
         slot = np.zeros(cap, dtype=np.int32)
@@ -192,29 +199,32 @@ class Tracker:
         status = np.zeros(cap, dtype=np.int32)
         _lib.check(self._lib.mht_forest_tracks(self._forest, cap, C.byref(n), _lib.ptr(slot), _lib.ptr(x), _lib.ptr(P),
                                                _lib.ptr(cn), _lib.ptr(meas), _lib.ptr(status)))
-        assert list(slot[:n.value]) == self._slots, "forest/track bookkeeping out of sync"
-        scanNumber = len(self.__scanHistory__)
-        zs = np.asarray(scanList.measurements)
-        nodes, keep = [], []
-        for i, s in enumerate(self._slots):
-            root = self._slot_info[s]
-            m = int(meas[i])
-            node = Target(scanList.time, scanNumber, x[i].copy(), P[i].copy(), ID=root.ID, P_d=root.P_d,
-                          measurementNumber=m, measurement=(zs[m - 1] if m > 0 else None),
-                          cumulativeNLLR=float(cn[i]), status=STATUS_TAGS[int(status[i])],
-                          parent_loader=self._make_parent_loader(s))
-            if status[i] != 0:
-                _ = node.parent          # materialise the history while the window is still on the device
-                self.__terminatedTargets__.append(node)
-            else:
-                nodes.append(node)
-                keep.append(i)
-        self._slots = [self._slots[i] for i in keep]
-        self.__targetList__ = [self.__targetList__[i] for i in keep]
-        self.__targetWindowSize__ = [self.__targetWindowSize__[i] for i in keep]
-        self.__trackNodes__ = np.empty(len(nodes), dtype=np.dtype(object))
-        for i, nd in enumerate(nodes):
-            self.__trackNodes__[i] = nd
+        k = n.value
+        assert k == len(self._slots) and np.array_equal(slot[:k], self._slots), "forest/track bookkeeping out of sync"
+        self._last = (scanList, len(self.__scanHistory__), x, P, cn, meas, status)
+        dead = np.flatnonzero(status[:k] != 0)
+        for i in dead:
+            node = self._make_node(int(i), self._slots[i])
+            _ = node.parent          # materialise the history while the window is still on the device
+            self.__terminatedTargets__.append(node)
+        if len(dead):
+            keep = [i for i in range(k) if status[i] == 0]
+            self._slots = [self._slots[i] for i in keep]
+            self.__targetList__ = [self.__targetList__[i] for i in keep]
+            self.__targetWindowSize__ = [self.__targetWindowSize__[i] for i in keep]
+            self._live_rows = keep
+        else:
+            self._live_rows = None
+        self.__trackNodes__ = None       # built on demand
+
+    def _make_node(self, row, slot):
+        scanList, scanNumber, x, P, cn, meas, status = self._last
+        root = self._slot_info[slot]
+        m = int(meas[row])
+        return Target(scanList.time, scanNumber, x[row].copy(), P[row].copy(), ID=root.ID, P_d=root.P_d,
+                      measurementNumber=m, measurement=(np.asarray(scanList.measurements)[m - 1] if m > 0 else None),
+                      cumulativeNLLR=float(cn[row]), status=STATUS_TAGS[int(status[row])],
+                      parent_loader=self._make_parent_loader(slot))
 
     def _history(self, slot):
         cap = 64
@@ -263,6 +273,13 @@ class Tracker:
 
     # ------------------------------------------------------------------------------------------
     def getTrackNodes(self):
+        """Selected leaf `Target` of every live track (tracker.py:976), in track order."""
+        if self.__trackNodes__ is None:
+            rows = self._live_rows if self._live_rows is not None else range(len(self._slots))
+            nodes = np.empty(len(self._slots), dtype=np.dtype(object))
+            for i, (row, slot) in enumerate(zip(rows, self._slots)):
+                nodes[i] = self._make_node(row, slot)
+            self.__trackNodes__ = nodes
         return self.__trackNodes__
 
     def getLeafNodes(self, trackIndex):
@@ -290,9 +307,10 @@ class Tracker:
         return " ".join("%s %.2fms" % (k, 1e3 * v) for k, v in self.toc.items())
 
     def _checkTrackerIntegrity(self):
-        assert len(self.__trackNodes__) == len(self.__targetList__) == len(self._slots)
-        assert len({n.ID for n in self.__trackNodes__}) == len(self.__trackNodes__)
-        if len(self.__trackNodes__):
-            assert len({n.scanNumber for n in self.__trackNodes__}) == 1
-        for n in self.__trackNodes__:
+        nodes = self.getTrackNodes()
+        assert len(nodes) == len(self.__targetList__) == len(self._slots)
+        assert len({n.ID for n in nodes}) == len(nodes)
+        if len(nodes):
+            assert len({n.scanNumber for n in nodes}) == 1
+        for n in nodes:
             assert np.isfinite(n.cumulativeNLLR)
