@@ -24,6 +24,7 @@
 // Sums that steer the iteration are accumulated in 2^-34 fixed point so the result does not depend
 // on atomic ordering.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "assoc.cuh"
 
@@ -232,42 +233,93 @@ __device__ __forceinline__ bool du_skip(const ColView &c, const AssocWork &w) {
     return w.info[0] || (c.idx && w.act_n[2]);
 }
 
-__device__ __forceinline__ void du_trees_body(ColView c, AssocWork w) {
-    if (du_skip(c, w)) return;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
-        if (w.tstart[t] < 0) continue;
-        const int cl = w.uf[t];
-        if (w.cl_done[cl]) continue;
-        const int j = w.targ[t];
-        w.freq[j] += 1;  // ergodic primal estimate: how often this column is the tree's Lagrangian choice
-        atomicAdd((unsigned long long *)&w.cl_m[cl], (unsigned long long)to_fix(key_f64(w.tmin[t])));
-        atomicAdd((unsigned long long *)&w.cl_cost[cl], (unsigned long long)to_fix(col_cost(c, j, t)));
-        for (int k = 0; k < c.width; ++k) {
-            const int r = c.rows[(long long)k * c.stride + j];
-            if (r >= 0) atomicAdd(&w.usage[r], 1);
-        }
+// warp-aggregated accumulation into per-cluster sums: when every active lane targets the same cluster
+// (the normal case: one giant cluster, or consecutive trees/rows of one cluster) the warp reduces first
+// and issues ONE atomic; otherwise lanes fall back to individual atomics.  Integer adds: order-free.
+__device__ __forceinline__ void warp_add_ll(long long *base, int cl, long long v, bool active) {
+    const unsigned mask = __ballot_sync(0xffffffffu, active);
+    if (!mask) return;
+    const int leader = __ffs(mask) - 1;
+    const int cl0 = __shfl_sync(0xffffffffu, cl, leader);
+    if (__all_sync(0xffffffffu, !active || cl == cl0)) {
+        long long x = active ? v : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == leader) atomicAdd((unsigned long long *)&base[cl0], (unsigned long long)x);
+    } else if (active) {
+        atomicAdd((unsigned long long *)&base[cl], (unsigned long long)v);
     }
 }
-__global__ void du_trees_kernel(ColView c, AssocWork w) { du_trees_body(c, w); }
+__device__ __forceinline__ void warp_add_i(int *base, int cl, int v, bool active) {
+    const unsigned mask = __ballot_sync(0xffffffffu, active);
+    if (!mask) return;
+    const int leader = __ffs(mask) - 1;
+    const int cl0 = __shfl_sync(0xffffffffu, cl, leader);
+    if (__all_sync(0xffffffffu, !active || cl == cl0)) {
+        int x = active ? v : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == leader && x) atomicAdd(&base[cl0], x);
+    } else if (active && v) {
+        atomicAdd(&base[cl], v);
+    }
+}
 
+__device__ __forceinline__ void du_trees_body(ColView c, AssocWork w) {
+    if (du_skip(c, w)) return;
+    const int T = c.n_trees;
+    const int Tround = (T + 31) & ~31;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < Tround; t += gridDim.x * blockDim.x) {
+        int cl = 0;
+        bool active = t < T && w.tstart[t] >= 0;
+        if (active) {
+            cl = w.uf[t];
+            active = !w.cl_done[cl];
+        }
+        long long m = 0, cost = 0;
+        if (active) {
+            const int j = w.targ[t];
+            w.freq[j] += 1;  // ergodic primal estimate: how often this column is the tree's Lagrangian choice
+            m = to_fix(key_f64(w.tmin[t]));
+            cost = to_fix(col_cost(c, j, t));
+            for (int k = 0; k < c.width; ++k) {
+                const int r = c.rows[(long long)k * c.stride + j];
+                if (r >= 0) atomicAdd(&w.usage[r], 1);
+            }
+        }
+        warp_add_ll(w.cl_m, cl, m, active);
+        warp_add_ll(w.cl_cost, cl, cost, active);
+    }
+}
+
+__global__ void du_trees_kernel(ColView c, AssocWork w) { du_trees_body(c, w); }
 
 __device__ __forceinline__ void du_rows_body(ColView c, AssocWork w) {
     if (du_skip(c, w)) return;
     const int nr = *w.row_n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += gridDim.x * blockDim.x) {
-        const int r = w.row_list[i];
-        const int cl = w.uf[w.row_owner[r]];
-        if (w.cl_done[cl]) continue;
-        int g = w.usage[r] - 1;
-        const double ur = w.u[r];
-        if (ur <= 0.0 && g < 0) g = 0;
-        w.usage[r] = g;
-        if (g) atomicAdd(&w.cl_nrm[cl], g * g);
-        if (ur > 0.0) atomicAdd((unsigned long long *)&w.cl_u[cl], (unsigned long long)to_fix(ur));
+    const int nround = (nr + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+        int cl = 0, g = 0;
+        long long uf = 0;
+        bool active = i < nr;
+        if (active) {
+            const int r = w.row_list[i];
+            cl = w.uf[w.row_owner[r]];
+            active = !w.cl_done[cl];
+            if (active) {
+                g = w.usage[r] - 1;
+                const double ur = w.u[r];
+                if (ur <= 0.0 && g < 0) g = 0;
+                w.usage[r] = g;
+                if (ur > 0.0) uf = to_fix(ur);
+            }
+        }
+        warp_add_i(w.cl_nrm, cl, g * g, active);
+        warp_add_ll(w.cl_u, cl, uf, active);
     }
 }
-__global__ void du_rows_kernel(ColView c, AssocWork w) { du_rows_body(c, w); }
 
+__global__ void du_rows_kernel(ColView c, AssocWork w) { du_rows_body(c, w); }
 
 __device__ __forceinline__ void du_decide_body(ColView c, AssocWork w) {
     if (du_skip(c, w)) return;
@@ -980,6 +1032,9 @@ __global__ void __launch_bounds__(32) branch_bound_kernel(ColView c, AssocWork w
                 }
         }
         const double Lcomp = sum_m - sum_u;
+        // the single-thread search is only worth its latency on small components
+        const unsigned long long node_budget =
+            (unsigned long long)(k <= 32 ? budget : (k <= 128 ? budget / 8 : budget / 64));
         unsigned long long nodes = 0;
         int depth = 0;
         pos[0] = 0;
@@ -1019,7 +1074,7 @@ __global__ void __launch_bounds__(32) branch_bound_kernel(ColView c, AssocWork w
                     }
                 continue;
             }
-            if (++nodes > (unsigned long long)budget) {
+            if (++nodes > node_budget) {
                 exhausted = true;
                 break;
             }
@@ -1225,7 +1280,8 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
         ColView a = c;
         a.idx = w.act_col;
         a.n_ptr = w.act_n;
-        const int act_grid = kSMs;
+        static const int act_grid_env = getenv("MHT_ACT_GRID") ? atoi(getenv("MHT_ACT_GRID")) : 2 * kSMs;
+        const int act_grid = act_grid_env;
         for (int round = 0; round < kSiftRounds; ++round) {
             if (round) sift_rearm_kernel<<<1, 1024, 0, s>>>(c, w);
             dual_rc_kernel<true><<<grid_dim, 256, 0, s>>>(c, w);

@@ -6,8 +6,16 @@ import sys
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 5]
 hdr = rows[0]
 ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+body = rows[1:]
+if "--scan" in sys.argv:   # keep only the n-th scan (1-based); a scan starts at live_scan_kernel
+    want = int(sys.argv[sys.argv.index("--scan") + 1])
+    starts = [i for i, r in enumerate(body) if "live_scan_kernel" in r[ki]]
+    lo = starts[want - 1]
+    hi = starts[want] if want < len(starts) else len(body)
+    body = body[lo:hi]
+    print("scan %d of %d: launches %d..%d" % (want, len(starts), lo, hi))
 agg = collections.OrderedDict()
-for r in rows[1:]:
+for r in body:
     name = r[ki].split("(")[0].replace("void ", "").replace("mht::", "")
     v = float(r[vi].replace(",", ""))
     v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(r[ui], 1.0)
