@@ -259,6 +259,12 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = bytes_gate / (ms_gate * 1e-3) / 1e9
+        traffic = None   # measured DRAM bytes of the gate stage (ncu capture in profiles/), scaled by children
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))["gate_stage"]
+            traffic = tr["dram_bytes"] / tr["n_children"] * float(np.mean([d["n_children"] for d in timed]))
+        except Exception:
+            pass
         line = {
             "metric": "scans/sec @ 1k targets, 5k meas/scan", "value": value, "unit": "scans/s", "n_gpus": world,
             "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True,
@@ -270,7 +276,7 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "gate stage (forest_count_kernel + forest_emit_kernel)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                         "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "bytes_per_launch": bytes_gate, "ms_per_launch": ms_gate},
             "stage_ms": {k: float(np.mean([d[k] for d in timed])) for k in
                          ("ms_gate", "ms_cluster", "ms_assoc", "ms_prune", "ms_total")},
