@@ -148,6 +148,8 @@ typedef struct mht_scan_info {
     float ms_gate, ms_cluster, ms_assoc, ms_prune; /* CUDA-event stage times */
     float ms_total, ms_h2d;  /* whole scan on the device (first kernel -> results on host); scan upload */
     int64_t n_active;        /* columns on the dual iteration's active list (0 = all columns iterate) */
+    int32_t max_component;   /* trees in the largest component handed to the exact search */
+    int32_t n_components;    /* multi-tree components handed to the exact search */
 } mht_scan_info;
 
 int mht_forest_create(const mht_forest_config *cfg, mht_forest **out);

@@ -47,7 +47,7 @@ class ScanInfo(C.Structure):
                 ("n_dead", C.c_int32), ("dual_iters", C.c_int32), ("certified", C.c_int32),
                 ("n_candidates", C.c_int64), ("bb_nodes", C.c_int64), ("lower_bound", C.c_double),
                 ("objective", C.c_double), ("ms_gate", C.c_float), ("ms_cluster", C.c_float),
-                ("ms_assoc", C.c_float), ("ms_prune", C.c_float), ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("n_active", C.c_int64)]
+                ("ms_assoc", C.c_float), ("ms_prune", C.c_float), ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("n_active", C.c_int64), ("max_component", C.c_int32), ("n_components", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -54,7 +54,7 @@ __device__ __forceinline__ double col_cost(const ColView &c, int j, int t) {
 // ------------------------------------------------------------------------------------------------
 __global__ void assoc_init_kernel(ColView c, AssocWork w, int *tstart, int *tend, int warm) {
     const int T = c.n_trees, R = c.n_rows;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max(T + 1, R); i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max(max(T + 1, R), kAssocInfo); i += gridDim.x * blockDim.x) {
         if (i < T) {
             tstart[i] = -1;
             tend[i] = -1;
@@ -778,6 +778,7 @@ __global__ void __launch_bounds__(1024, 1) final_prepare_kernel(ColView c, Assoc
         w.usage[r] = 0;
         w.row_mark[r] = -1;
         w.row_taken[r] = 0;
+        w.row_holder[r] = -1;
     }
     for (int t = threadIdx.x; t < c.n_trees; t += blockDim.x) {
         w.tmin[t] = kKeyInf;
@@ -903,8 +904,8 @@ __global__ void __launch_bounds__(256) cand_fill_kernel(ColView c, AssocWork w) 
     }
 }
 
-// per tree: sort candidates by (excess, column); union trees that share a row among candidates
-__global__ void cand_sort_union_kernel(ColView c, AssocWork w) {
+// per tree: sort candidates by (excess, column)
+__global__ void cand_sort_kernel(ColView c, AssocWork w) {
     if (w.info[6]) return;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
         const int cnt = w.cand_cnt[t];
@@ -920,6 +921,31 @@ __global__ void cand_sort_union_kernel(ColView c, AssocWork w) {
             }
             v[p + 1] = key;
         }
+    }
+}
+
+// ---- dominance reduction of the candidate lists ----------------------------------------------------
+// A row is CONTESTED when candidates of two or more trees use it.  Within a tree, candidate a dominates
+// candidate b when it is not more expensive and its contested rows are a subset of b's: any solution
+// using b stays feasible and gets no worse with a (a's other rows are wanted by nobody else).  Removing
+// dominated candidates keeps an optimal solution and collapses the "independent cheap alternatives" that
+// make plain enumeration explode; rows stop being contested as lists shrink, so the pass is repeated.
+__global__ void contest_reset_kernel(AssocWork w) {
+    if (w.info[6]) return;
+    const int nr = *w.row_n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += gridDim.x * blockDim.x) {
+        const int r = w.row_list[i];
+        w.row_mark[r] = -1;
+        w.row_cont[r] = 0;
+    }
+}
+
+// also used for the component union (uf != null): trees sharing a row among surviving candidates
+__global__ void contest_mark_kernel(ColView c, AssocWork w, int *uf) {
+    if (w.info[6]) return;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
+        const int cnt = w.cand_cnt[t];
+        const int *v = w.cand_col + w.cand_off[t];
         for (int i = 0; i < cnt; ++i) {
             const int j = v[i];
             for (int k = 0; k < c.width; ++k) {
@@ -930,9 +956,69 @@ __global__ void cand_sort_union_kernel(ColView c, AssocWork w) {
                     o = atomicCAS(&w.row_mark[r], -1, t);
                     if (o < 0) o = t;
                 }
-                if (o != t) uf_union(w.comp_uf, t, o);
+                if (o != t) {
+                    w.row_cont[r] = 1;
+                    if (uf) uf_union(uf, t, o);
+                }
             }
         }
+    }
+}
+
+__device__ __forceinline__ bool contested_subset(const ColView &c, const int *row_cont, int a, int b) {
+    for (int k = 0; k < c.width; ++k) {
+        const int r = c.rows[(long long)k * c.stride + a];
+        if (r < 0 || !row_cont[r]) continue;
+        bool found = false;
+        for (int q = 0; q < c.width; ++q) found = found || c.rows[(long long)q * c.stride + b] == r;
+        if (!found) return false;
+    }
+    return true;
+}
+
+__global__ void cand_dominance_kernel(ColView c, AssocWork w) {
+    if (w.info[6]) return;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
+        const int cnt = w.cand_cnt[t];
+        if (cnt < 2) continue;
+        int *v = w.cand_col + w.cand_off[t];
+        unsigned long long drop[(kMaxCandPerTree + 63) / 64] = {0ull};
+        for (int ib = 0; ib < cnt; ++ib) {
+            const int b = v[ib];
+            const double cb = col_cost(c, b, t);
+            for (int ia = 0; ia < cnt; ++ia) {
+                if (ia == ib) continue;
+                const int a = v[ia];
+                const double ca = col_cost(c, a, t);
+                if (!(ca < cb || (ca == cb && a > b))) continue;   // ties: the later leaf wins, like the reference
+                if (contested_subset(c, w.row_cont, a, b)) {
+                    drop[ib >> 6] |= 1ull << (ib & 63);
+                    break;
+                }
+            }
+        }
+        // the incumbent must stay inside the lists (components are only independent over listed columns):
+        // if it was dominated, a surviving dominator replaces it -- feasible and not more expensive
+        const int inc = w.sel[t];
+        for (int ib = 0; ib < cnt; ++ib) {
+            if (v[ib] != inc || !(drop[ib >> 6] >> (ib & 63) & 1ull)) continue;
+            const double cb = col_cost(c, inc, t);
+            bool replaced = false;
+            for (int ia = 0; ia < cnt && !replaced; ++ia) {
+                if (drop[ia >> 6] >> (ia & 63) & 1ull) continue;
+                const int a = v[ia];
+                const double ca = col_cost(c, a, t);
+                if ((ca < cb || (ca == cb && a > inc)) && contested_subset(c, w.row_cont, a, inc)) {
+                    w.sel[t] = a;
+                    replaced = true;
+                }
+            }
+            if (!replaced) drop[ib >> 6] &= ~(1ull << (ib & 63));
+        }
+        int n = 0;
+        for (int i = 0; i < cnt; ++i)
+            if (!(drop[i >> 6] >> (i & 63) & 1ull)) v[n++] = v[i];
+        w.cand_cnt[t] = n;
     }
 }
 
@@ -942,9 +1028,15 @@ __global__ void __launch_bounds__(1024, 1) comp_build_kernel(ColView c, AssocWor
     const int T = c.n_trees;
     __shared__ int ncomp, maxc;
     if (threadIdx.x == 0) ncomp = maxc = 0;
+    __shared__ int nsurv;
+    if (threadIdx.x == 0) nsurv = 0;
+    __syncthreads();
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
         w.comp_cnt[t] = 0;
-        if (w.cand_cnt[t] > 0) w.comp_uf[t] = uf_find(w.comp_uf, t);
+        if (w.cand_cnt[t] > 0) {
+            w.comp_uf[t] = uf_find(w.comp_uf, t);
+            atomicAdd(&nsurv, w.cand_cnt[t]);
+        }
     }
     __syncthreads();
     for (int t = threadIdx.x; t < T; t += blockDim.x)
@@ -967,6 +1059,8 @@ __global__ void __launch_bounds__(1024, 1) comp_build_kernel(ColView c, AssocWor
         ncomp = k;
         w.info[4] = k;
         w.info[9] = maxc;
+        w.info[13] = w.info[3];   // candidates after reduced-cost fixing
+        w.info[3] = nsurv;        // ... and after dominance reduction
     }
     __syncthreads();
     for (int t = threadIdx.x; t < T; t += blockDim.x) w.cand_fill[t] = 0;  // reuse as per-component cursor
@@ -989,6 +1083,110 @@ __global__ void __launch_bounds__(1024, 1) comp_build_kernel(ColView c, AssocWor
                 }
             }
             w.sel[t] = best;
+        }
+    }
+}
+
+// one thread per component: first-improvement local search on the incumbent over the candidate columns.
+//   1-opt: a tree switches to a cheaper candidate whose rows are free;
+//   2-opt: a tree takes a candidate that collides with exactly ONE other tree, which moves to its best
+//          candidate that is free afterwards, when the pair's total cost drops.
+// Tightens the upper bound before the exact search (the greedy primal is the weak side on big clusters).
+__global__ void __launch_bounds__(32) local_search_kernel(ColView c, AssocWork w, int max_sweeps) {
+    if (w.info[6]) return;
+    const int ncomp = w.info[4];
+    for (int comp = blockIdx.x; comp < ncomp; comp += gridDim.x) {
+        if (threadIdx.x != 0) continue;
+        const int off = w.comp_off[comp], k = w.comp_off[comp + 1] - off;
+        const int *trees = w.comp_trees + off;
+        for (int i = 0; i < k; ++i) {
+            const int t = trees[i], j = w.sel[t];
+            for (int kk = 0; kk < c.width; ++kk) {
+                const int r = c.rows[(long long)kk * c.stride + j];
+                if (r >= 0) w.row_holder[r] = t;
+            }
+        }
+        for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+            bool improved = false;
+            for (int i = 0; i < k; ++i) {
+                const int t = trees[i];
+                const int cur = w.sel[t];
+                const double cur_cost = col_cost(c, cur, t);
+                const int *v = w.cand_col + w.cand_off[t];
+                for (int q = 0; q < w.cand_cnt[t]; ++q) {
+                    const int j = v[q];
+                    if (j == cur) continue;
+                    const double dt = col_cost(c, j, t) - cur_cost;
+                    int other = -1, nother = 0;
+                    for (int kk = 0; kk < c.width && nother < 2; ++kk) {
+                        const int r = c.rows[(long long)kk * c.stride + j];
+                        if (r < 0) continue;
+                        const int h = w.row_holder[r];
+                        if (h >= 0 && h != t && h != other) {
+                            other = h;
+                            ++nother;
+                        }
+                    }
+                    int j2 = -1;
+                    double d2 = 0.0;
+                    if (nother == 0) {
+                        if (dt >= -1e-12) continue;
+                    } else if (nother == 1) {
+                        const int cur2 = w.sel[other];
+                        const double cur2_cost = col_cost(c, cur2, other);
+                        const int *v2 = w.cand_col + w.cand_off[other];
+                        double best2 = 1e300;
+                        for (int q2 = 0; q2 < w.cand_cnt[other]; ++q2) {
+                            const int cand2 = v2[q2];
+                            const double cc = col_cost(c, cand2, other);
+                            if (cc >= best2) continue;
+                            bool ok = true;
+                            for (int kk = 0; kk < c.width && ok; ++kk) {
+                                const int r2 = c.rows[(long long)kk * c.stride + cand2];
+                                if (r2 < 0) continue;
+                                for (int k3 = 0; k3 < c.width; ++k3)   // j takes its rows
+                                    if (c.rows[(long long)k3 * c.stride + j] == r2) ok = false;
+                                const int h = w.row_holder[r2];
+                                if (h >= 0 && h != other && h != t) ok = false;   // rows t holds now are released
+                            }
+                            if (ok) {
+                                best2 = cc;
+                                j2 = cand2;
+                            }
+                        }
+                        if (j2 < 0) continue;
+                        d2 = best2 - cur2_cost;
+                        if (dt + d2 >= -1e-12) continue;
+                    } else {
+                        continue;
+                    }
+                    // apply: release, then take
+                    for (int kk = 0; kk < c.width; ++kk) {
+                        const int r = c.rows[(long long)kk * c.stride + cur];
+                        if (r >= 0) w.row_holder[r] = -1;
+                    }
+                    if (j2 >= 0) {
+                        const int cur2 = w.sel[other];
+                        for (int kk = 0; kk < c.width; ++kk) {
+                            const int r = c.rows[(long long)kk * c.stride + cur2];
+                            if (r >= 0) w.row_holder[r] = -1;
+                        }
+                        for (int kk = 0; kk < c.width; ++kk) {
+                            const int r = c.rows[(long long)kk * c.stride + j2];
+                            if (r >= 0) w.row_holder[r] = other;
+                        }
+                        w.sel[other] = j2;
+                    }
+                    for (int kk = 0; kk < c.width; ++kk) {
+                        const int r = c.rows[(long long)kk * c.stride + j];
+                        if (r >= 0) w.row_holder[r] = t;
+                    }
+                    w.sel[t] = j;
+                    improved = true;
+                    break;   // re-evaluate this tree from its new incumbent on the next sweep
+                }
+            }
+            if (!improved) break;
         }
     }
 }
@@ -1034,7 +1232,7 @@ __global__ void __launch_bounds__(32) branch_bound_kernel(ColView c, AssocWork w
         const double Lcomp = sum_m - sum_u;
         // the single-thread search is only worth its latency on small components
         const unsigned long long node_budget =
-            (unsigned long long)(k <= 32 ? budget : (k <= 128 ? budget / 8 : budget / 64));
+            (unsigned long long)(k <= 64 ? budget : budget / 64);
         unsigned long long nodes = 0;
         int depth = 0;
         pos[0] = 0;
@@ -1169,6 +1367,8 @@ static int64_t carve_all(Carver &cv, int64_t cap_cols, int64_t T, int64_t R, int
     d.row_bid = cv.take<unsigned long long>(R);
     d.row_taken = cv.take<int>(R);
     d.row_mark = cv.take<int>(R);
+    d.row_cont = cv.take<int>(R);
+    d.row_holder = cv.take<int>(R);
     d.row_list = cv.take<int>(R);
     d.row_n = cv.take<int>(4);
     d.cap_act = cap_cols < (1 << 20) ? cap_cols : (cap_cols / 8 > (1 << 20) ? cap_cols / 8 : (1 << 20));
@@ -1206,7 +1406,8 @@ void assoc_carve(void *d_work, int64_t cap_cols, int64_t T, int64_t R, int64_t c
 
 int assoc_begin(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s, bool warm) {
     (void)grid_dim;
-    const int n = (c.n_trees + 1 > c.n_rows ? c.n_trees + 1 : c.n_rows);
+    int n = (c.n_trees + 1 > c.n_rows ? c.n_trees + 1 : c.n_rows);
+    if (n < kAssocInfo) n = kAssocInfo;  // the status words are cleared by the same kernel
     assoc_init_kernel<<<(n + 255) / 256, 256, 0, s>>>(c, w, w.tstart, g_tend, warm ? 1 : 0);
     MHT_CUDA(cudaGetLastError());
     return MHT_OK;
@@ -1274,7 +1475,9 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
     dual_arg_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
     dual_update(c, w, s);
     if (!sift) {
-        if (int rc = dual_loop(c, w, max_iters, grid_dim, s)) return rc;
+        // small problem: iterations cost ~25 us each, so give the bound 4x the budget (the loop leaves as soon
+        // as every cluster is settled or nothing has moved for kStallStop iterations)
+        if (int rc = dual_loop(c, w, 4 * max_iters, grid_dim, s)) return rc;
     } else {
         // sifting: price all columns, iterate on the active list, re-price; kSiftRounds times
         ColView a = c;
@@ -1301,8 +1504,19 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
     cand_count_kernel<<<grid_dim, 256, 0, s>>>(c, w);
     cand_scan_kernel<<<1, 1024, 0, s>>>(c, w);
     cand_fill_kernel<<<grid_dim, 256, 0, s>>>(c, w);
-    cand_sort_union_kernel<<<(c.n_trees + 127) / 128, 128, 0, s>>>(c, w);
+    {
+        const int tb = (c.n_trees + 127) / 128, rb = (c.n_rows + 255) / 256 < 1024 ? (c.n_rows + 255) / 256 : 1024;
+        cand_sort_kernel<<<tb, 128, 0, s>>>(c, w);
+        for (int round = 0; round < 3; ++round) {
+            contest_reset_kernel<<<rb, 256, 0, s>>>(w);
+            contest_mark_kernel<<<tb, 128, 0, s>>>(c, w, nullptr);
+            cand_dominance_kernel<<<tb, 128, 0, s>>>(c, w);
+        }
+        contest_reset_kernel<<<rb, 256, 0, s>>>(w);
+        contest_mark_kernel<<<tb, 128, 0, s>>>(c, w, w.comp_uf);
+    }
     comp_build_kernel<<<1, 1024, 0, s>>>(c, w);
+    local_search_kernel<<<kSMs * 4, 32, 0, s>>>(c, w, 50);
     branch_bound_kernel<<<kSMs * 4, 32, 0, s>>>(c, w, bb_budget, g_fscratch);
     final_objective_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
     MHT_CUDA(cudaGetLastError());

@@ -52,6 +52,8 @@ struct AssocWork {
     unsigned long long *row_bid;
     int *row_taken;
     int *row_mark;
+    int *row_cont;             // [R] 1 = candidates of two or more trees use the row
+    int *row_holder;           // [R] local search: tree currently using the row (-1 free)
     int *row_list;             // [R] rows touched by at least one column (order irrelevant)
     int *row_n;                // device: entries of row_list
     int *tstart;               // [T] first column of each tree (-1: the tree has no columns)

@@ -821,6 +821,8 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
         info->lower_bound = st.lower_bound;
         info->objective = st.objective;
         info->n_active = sift ? st.assoc[12] : 0;
+        info->max_component = st.assoc[9];
+        info->n_components = st.assoc[4];
         cudaEventElapsedTime(&info->ms_gate, f->ev[0], f->ev[1]);
         cudaEventElapsedTime(&info->ms_cluster, f->ev[1], f->ev[5]);
         cudaEventElapsedTime(&info->ms_assoc, f->ev[5], f->ev[2]);

@@ -82,3 +82,8 @@ def test_replay_cfg2():
 
 def test_replay_cfg3_head():
     replay("cfg3_head", n_scans=2)
+
+
+def test_replay_cfg3_lowclutter():
+    """1000 targets, 10x less clutter: scans 1-2 (scan 3 needs ~3 min of HiGHS; the GPU test replays it)."""
+    replay("cfg3_lowclutter", n_scans=2)
