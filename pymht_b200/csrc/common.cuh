@@ -62,9 +62,8 @@ __device__ __forceinline__ void mm_f32(const float *a, const float *b, float *c)
         }
 }
 
-template <bool WANT_UPDATE>
-__device__ __forceinline__ void leaf_kf(const mht_model &m, const double x0[4], const float P0[16], double Pd,
-                                        LeafKF &o) {
+// State part (float64): x_bar = A x, z_hat = C x_bar  (kalman.py:55-59, :88)
+__device__ __forceinline__ void state_kf(const mht_model &m, const double x0[4], LeafKF &o) {
     // x_bar = A x  (A float32 upcast; dgemm-order FMA chain)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -73,12 +72,6 @@ __device__ __forceinline__ void leaf_kf(const mht_model &m, const double x0[4], 
         for (int k = 0; k < 4; ++k) acc = fma((double)m.A[i * 4 + k], x0[k], acc);
         o.xbar[i] = acc;
     }
-    // P_bar = (A P) A^T + Q
-    float AP[16];
-    mm_f32<4, 4, 4, false>(m.A, P0, AP);
-    mm_f32<4, 4, 4, true>(AP, m.A, o.Pbar);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) o.Pbar[i] = o.Pbar[i] + m.Q[i];
     // z_hat = C x_bar
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -87,6 +80,19 @@ __device__ __forceinline__ void leaf_kf(const mht_model &m, const double x0[4], 
         for (int k = 0; k < 4; ++k) acc = fma((double)m.C[i * 4 + k], o.xbar[k], acc);
         o.zhat[i] = acc;
     }
+}
+
+// Covariance part (float32 chain): P_bar, S, S^-1, gate box, NLLR log term, K, P_hat.  Depends on
+// (P0, P_d) only -- never on the state -- which is what lets the forest evaluate it once per
+// hit/miss pattern of a tree instead of once per leaf (forest.cu, pat_table_kernel).
+template <bool WANT_UPDATE>
+__device__ __forceinline__ void cov_kf(const mht_model &m, const float P0[16], double Pd, LeafKF &o) {
+    // P_bar = (A P) A^T + Q
+    float AP[16];
+    mm_f32<4, 4, 4, false>(m.A, P0, AP);
+    mm_f32<4, 4, 4, true>(AP, m.A, o.Pbar);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o.Pbar[i] = o.Pbar[i] + m.Q[i];
     // S = (C P_bar) C^T + R
     float CP[8], S[4];
     mm_f32<2, 4, 4, false>(m.C, o.Pbar, CP);
@@ -130,6 +136,13 @@ __device__ __forceinline__ void leaf_kf(const mht_model &m, const double x0[4], 
 #pragma unroll
         for (int i = 0; i < 16; ++i) o.Phat[i] = o.Pbar[i] - KCP[i];
     }
+}
+
+template <bool WANT_UPDATE>
+__device__ __forceinline__ void leaf_kf(const mht_model &m, const double x0[4], const float P0[16], double Pd,
+                                        LeafKF &o) {
+    state_kf(m, x0, o);
+    cov_kf<WANT_UPDATE>(m, P0, Pd, o);
 }
 
 // d2 = sum((z~ @ S^-1) * z~)  (kalman.py:25-28): two FMA-chain products, then mul, mul, add.

@@ -4,8 +4,12 @@
 // Layout.  One LEVEL per scan (ring of N+2 levels).  A level holds the hypotheses created by that
 // scan as structure-of-arrays in the reference's DFS leaf order (Target.getLeafNodes,
 // pymht/pyTarget.py:461-471): x[4] f64, cNLLR f64, measurementNumber i32, tree i32, parent link i32.
-// Covariances are stored once per PARENT (P_bar for its miss child, P_hat shared by all its gated
-// children, exactly the sharing of pyTarget.py:239-254) instead of once per child.
+// Covariances are NOT stored per node: with the reference's constant A, Q, C, R (one shared model for all
+// nodes, kalman.py:55-64,82-101) the covariance chain of a node depends only on its tree's root covariance
+// and on the hit/miss pattern of the path below the root, so every scan a small kernel evaluates the
+// float32 chain once per (tree, pattern) -- at most 2^N entries per tree -- into an L2-resident table of
+// S^-1, K, gate box and NLLR log term, and each leaf carries 16 bits of hit/miss history (`pat`).  The
+// values are bit-identical to evaluating the same chain per leaf.
 // Every leaf also carries its root->leaf measurement path as W = N+1 int32 "row planes"
 // (row = plane*max_meas + measurement index, -1 = miss): the association columns, the clusters and the
 // N-scan prune all stream these planes and never chase parent pointers.  Because children are written
@@ -26,10 +30,9 @@ struct Level {
     double2 *xb;     // [cap_nodes] (vx, vy)
     double *cnllr;   // [cap_nodes]
     int *meas;       // [cap_nodes]  measurementNumber (0 = miss / initial)
-    int *pidx;       // [cap_nodes]  index into this level's Pbar/Phat tables
+    int *pidx;       // [cap_nodes]  live index of the parent in the scan that created the node
     int *tree;       // [cap_nodes]
-    float *Pbar;     // [cap_ptab][16]
-    float *Phat;     // [cap_ptab][16]
+    unsigned short *pat;  // [cap_nodes] hit(1)/miss(0) history of the path, bit 0 = this node's scan
     int *tree_off;   // [T+1] children range per tree
     int *par_lo;     // [T+1] live range start (positions in the previous level) used to build this level
     int *par_off;    // [T+1] exclusive scan of live range lengths
@@ -38,6 +41,16 @@ struct Level {
 struct TreeState {   // device arrays, one entry per tree slot
     int *root_scan, *init_scan, *alive, *window, *live_lo, *live_hi;
     double *root_cnllr, *Pd, *miss;
+    float *rootP;    // [T][16] covariance of the current root node
+};
+
+// Per (tree, hit/miss pattern) gate quantities, heap-indexed: h = (1 << depth) | pattern bits.
+struct PatGate {
+    float si[4];     // S^-1
+    float K[8];      // Kalman gain
+    float logterm;   // ln(lambda_ex sqrt(det(2 pi S)) / P_d)
+    float pad[3];
+    double hx, hy;   // half extents of the gate ellipse's bounding box
 };
 
 struct TrackOut {    // per-scan results, device + pinned host mirror
@@ -67,7 +80,11 @@ struct mht_forest {
     mht_forest_config cfg;
     int W, nslots, T;          // planes, levels in the ring, tree slots in use
     int scan;                  // scans processed so far (= current level number)
-    int64_t cap_nodes, cap_par, cap_ptab;
+    int64_t cap_nodes, cap_par;
+    int PT;                    // pattern-table entries per tree = 2^(N+1)
+    PatGate *pt_gate;          // [max_trees][PT]
+    float *pt_P;               // [max_trees][PT][16] posterior covariance per pattern
+    int *tile_tree;            // [cap_par/kTile + 4] tree of the first live leaf of every tile
     int64_t bytes;
     char *arena;
     Level lv[MHT_MAX_WINDOW + 2];
@@ -91,7 +108,6 @@ struct mht_forest {
     std::vector<int> h_alive, h_root_scan, h_init_scan, h_last_pos;
     std::vector<std::vector<TrunkNode>> trunk;
     int64_t h_level_nodes;     // nodes in the current level (for initiate)
-    int64_t h_level_ptab;      // P-table entries in the current level
     std::vector<int> last_tracks;  // tree slots reported by the last scan
 };
 
@@ -113,8 +129,11 @@ struct ScanArgs {
     const double2 *gz;
     const int *gidx;
     const double2 *z;
-    int *count, *tile_sum;
+    int *count, *tile_sum, *tile_tree;
     int *d_np, *d_nc;
+    PatGate *pt_gate;
+    float *pt_P;
+    int PT, N;
     unsigned char *used;
     ScanStatus *status;
     long long cap_nodes, cap_par;
@@ -155,33 +174,89 @@ __global__ void __launch_bounds__(1024, 1) live_scan_kernel(ScanArgs a) {
     }
 }
 
-// live index -> (tree, position in the previous level)
-__device__ __forceinline__ void locate(const ScanArgs &a, int i, int &t, int &pos) {
-    int lo = 0, hi = a.T;  // largest t with par_off[t] <= i and a non-empty range
+// live index -> (tree, position in the previous level): largest t in [t_lo, t_hi] with par_off[t] <= i.
+// Callers pass the tree range of their tile (one tree almost always), so the search is 0-2 steps.
+__device__ __forceinline__ int locate_tree(const ScanArgs &a, int i, int t_lo, int t_hi) {
+    int lo = t_lo, hi = t_hi + 1;
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if (a.cur.par_off[mid] <= i) lo = mid; else hi = mid;
     }
-    t = lo;
-    pos = a.cur.par_lo[t] + (i - a.cur.par_off[t]);
+    return lo;
 }
 
-__device__ __forceinline__ void load_leaf(const ScanArgs &a, int pos, double x0[4], float P0[16]) {
+// Everything a leaf needs for the gate: float64 state prediction + its pattern-table entry.
+__device__ __forceinline__ const PatGate *load_leaf(const ScanArgs &a, int t, int pos, LeafKF &kf, int &ent) {
     const double2 x01 = a.prev.xa[pos], x23 = a.prev.xb[pos];
-    x0[0] = x01.x;
-    x0[1] = x01.y;
-    x0[2] = x23.x;
-    x0[3] = x23.y;
-    const float *tab = a.prev.meas[pos] ? a.prev.Phat : a.prev.Pbar;
-    const float4 *pp = (const float4 *)(tab + 16 * (size_t)a.prev.pidx[pos]);
+    const double x0[4] = {x01.x, x01.y, x23.x, x23.y};
+    state_kf(a.model, x0, kf);
+    const int d = min(a.N, (a.scan - 1) - a.ts.root_scan[t]);        // depth of the leaf below its root
+    const int h = (1 << d) | ((int)a.prev.pat[pos] & ((1 << d) - 1));
+    ent = t * a.PT + h;
+    const PatGate *e = a.pt_gate + ent;
+    const float4 si = __ldg((const float4 *)e->si);
+    kf.si[0] = (double)si.x;
+    kf.si[1] = (double)si.y;
+    kf.si[2] = (double)si.z;
+    kf.si[3] = (double)si.w;
+    kf.hx = __ldg(&e->hx);
+    kf.hy = __ldg(&e->hy);
+    return e;
+}
+
+// One CTA per tree: the float32 covariance chain for every hit/miss pattern of depth <= the tree's
+// current depth, level by level from the root covariance (kalman.py:55-64 predict, :82-101 precalc).
+__global__ void __launch_bounds__(128) pat_table_kernel(ScanArgs a) {
+    const int t = blockIdx.x;
+    if (a.status->overflow || t >= a.T || !a.ts.alive[t]) return;
+    const int dmax = min(a.N, (a.scan - 1) - a.ts.root_scan[t]);
+    float *P = a.pt_P + (size_t)t * a.PT * 16;
+    PatGate *G = a.pt_gate + (size_t)t * a.PT;
+    if (threadIdx.x < 16) P[16 + threadIdx.x] = a.ts.rootP[16 * t + threadIdx.x];
+    __syncthreads();
+    const double Pd = a.ts.Pd[t];
+    for (int d = 0; d <= dmax; ++d) {
+        for (int c = threadIdx.x; c < (1 << d); c += blockDim.x) {
+            const int h = (1 << d) | c;
+            float P0[16];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const float4 v = pp[r];
-        P0[4 * r] = v.x;
-        P0[4 * r + 1] = v.y;
-        P0[4 * r + 2] = v.z;
-        P0[4 * r + 3] = v.w;
+            for (int q = 0; q < 16; ++q) P0[q] = P[16 * h + q];
+            LeafKF kf;
+            cov_kf<true>(a.model, P0, Pd, kf);
+            PatGate g;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) g.si[q] = (float)kf.si[q];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) g.K[q] = kf.K[q];
+            g.logterm = (float)kf.logterm;
+            g.pad[0] = g.pad[1] = g.pad[2] = 0.0f;
+            g.hx = kf.hx;
+            g.hy = kf.hy;
+            G[h] = g;
+            if (d < dmax) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    P[16 * (2 * h) + q] = kf.Pbar[q];
+                    P[16 * (2 * h + 1) + q] = kf.Phat[q];
+                }
+            }
+        }
+        __syncthreads();
     }
+}
+
+// Posterior covariance of the node `depth` scans below a root with covariance rootP whose path has the
+// hit/miss bits `pat` (bit 0 = the node's own scan): the same chain pat_table_kernel evaluates.
+__device__ void chain_P(const mht_model &m, const float *rootP, unsigned pat, int depth, double Pd, float *out) {
+    float P[16];
+    for (int q = 0; q < 16; ++q) P[q] = rootP[q];
+    for (int j = depth - 1; j >= 0; --j) {
+        LeafKF kf;
+        cov_kf<true>(m, P, Pd, kf);
+        const bool hit = (pat >> j) & 1u;
+        for (int q = 0; q < 16; ++q) P[q] = hit ? kf.Phat[q] : kf.Pbar[q];
+    }
+    for (int q = 0; q < 16; ++q) out[q] = P[q];
 }
 
 __device__ __forceinline__ int block_scan_excl(int v, int *total) {
@@ -211,35 +286,39 @@ __device__ __forceinline__ int block_scan_excl(int v, int *total) {
     return excl;
 }
 
-// pass 1: children per live leaf (1 miss + gated) and per-tile sums
+// pass 1: children per live leaf (1 miss + gated): tile-local exclusive offsets + per-tile sums
 __global__ void __launch_bounds__(kTile) forest_count_kernel(ScanArgs a) {
     if (a.status->overflow) return;
     const int np = *a.d_np;
     const int ntiles = (np + kTile - 1) / kTile;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int i = tile * kTile + threadIdx.x;
+        // tree range of the tile (uniform searches: broadcast loads)
+        const int t_lo = locate_tree(a, tile * kTile, 0, a.T - 1);
+        const int t_hi = locate_tree(a, min(np, tile * kTile + kTile) - 1, t_lo, a.T - 1);
         int cnt = 0;
         if (i < np) {
-            int t, pos;
-            locate(a, i, t, pos);
-            double x0[4];
-            float P0[16];
-            load_leaf(a, pos, x0, P0);
+            const int t = locate_tree(a, i, t_lo, t_hi);
+            const int pos = a.cur.par_lo[t] + (i - a.cur.par_off[t]);
             LeafKF kf;
-            leaf_kf<false>(a.model, x0, P0, a.ts.Pd[t], kf);
+            int ent;
+            load_leaf(a, t, pos, kf, ent);
             cnt = 1;
             for_each_gated(*a.grid, a.cell_start, a.gz, kf, a.model.eta2,
                            [&](int, double, double, double) { ++cnt; });
-            a.count[i] = cnt;
         }
         int total;
-        block_scan_excl(cnt, &total);
-        if (threadIdx.x == 0) a.tile_sum[tile] = total;
+        const int excl = block_scan_excl(cnt, &total);
+        if (i < np) a.count[i] = excl;
+        if (threadIdx.x == 0) {
+            a.tile_sum[tile] = total;
+            a.tile_tree[tile] = t_lo;
+        }
         __syncthreads();
     }
 }
 
-// single CTA: exclusive scan of the tile sums; total children -> d_nc
+// single CTA: exclusive scan of the tile sums (tile_sum[n] = total); total children -> d_nc
 __global__ void __launch_bounds__(1024, 1) forest_scan_tiles_kernel(ScanArgs a) {
     if (a.status->overflow) return;
     const int np = *a.d_np;
@@ -260,139 +339,164 @@ __global__ void __launch_bounds__(1024, 1) forest_scan_tiles_kernel(ScanArgs a) 
     if (threadIdx.x == 0) {
         const bool over = carry > a.cap_nodes;
         *a.d_nc = over ? 0 : (int)carry;
+        a.tile_sum[n] = (int)min(carry, (long long)0x7fffffff);
         a.status->n_children = (int)min(carry, (long long)0x7fffffff);
         if (over) a.status->overflow = 2;
     }
 }
 
 // pass 2: write the new level.  Child order per leaf = [miss, gated by ascending measurement index]
-// (Target.spawnNewNodes, pyTarget.py:239-254).
-//   phase A (one thread per live leaf): Kalman quantities -> shared memory, P_bar/P_hat -> HBM, gated
-//            measurement indices (grid order) -> scratch at the leaf's child offset;
-//   phase B (one thread per CHILD, consecutive threads = consecutive children): rank the measurement
-//            among its siblings (ascending index), filter, score, and store every field coalesced.
-constexpr int kEmitD = 13;  // doubles per leaf in smem: xbar[4] zhat[2] si[4] logterm miss_cnllr base_cnllr
-__host__ __device__ inline size_t emit_smem_bytes(int W) {
-    return (size_t)kTile * (kEmitD * 8 + 8 * 4 + 4 + 4 * W) + 264 * 4;
+// (Target.spawnNewNodes, pyTarget.py:239-254).  Every WARP owns 32 consecutive live leaves and never
+// synchronises with the rest of its CTA (child offsets come from pass 1):
+//   phase A (lane = leaf): state prediction, pattern-table entry, inherited path planes, cluster links,
+//            gated measurement indices (grid order) -> warp staging (shared memory; HBM scratch if the
+//            warp has more than kStage children);
+//   phase B (lane = CHILD, consecutive lanes = consecutive children): rank the measurement among its
+//            siblings (ascending index), filter, score, and store every field coalesced.
+constexpr int kStage = 384;  // staged child slots per warp
+constexpr int kEmitD = 8;    // doubles per leaf in smem: xbar[4] zhat[2] base_cnllr miss_cnllr
+__host__ __device__ inline size_t emit_warp_bytes(int W) {
+    return (size_t)32 * kEmitD * 8 + (size_t)(3 + W) * 32 * 4 + 36 * 4 + kStage * 4;
 }
+__host__ __device__ inline size_t emit_smem_bytes(int W) { return (kTile / 32) * emit_warp_bytes(W); }
 
 __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, int *scratch) {
     if (a.status->overflow) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_d = (double *)smem_raw;                 // [kEmitD][kTile]
-    float *s_K = (float *)(s_d + kEmitD * kTile);      // [8][kTile]
-    int *s_tree = (int *)(s_K + 8 * kTile);            // [kTile]
-    int *s_off = s_tree + kTile;                       // [kTile+1] child offsets inside the tile
-    int *s_path = s_off + 264;                         // [W][kTile]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned char *wbase = smem_raw + (size_t)wib * emit_warp_bytes(a.W);
+    double *s_d = (double *)wbase;             // [kEmitD][32]
+    int *s_tree = (int *)(s_d + kEmitD * 32);  // [32]
+    int *s_ent = s_tree + 32;                  // [32] pattern-table entry
+    int *s_pat = s_ent + 32;                   // [32] hit/miss history of the leaf
+    int *s_off = s_pat + 32;                   // [33] child offsets inside the warp (+3 pad)
+    int *s_stage = s_off + 36;                 // [kStage]
+    int *s_path = s_stage + kStage;            // [W][32]
     const int np = *a.d_np;
     const int ntiles = (np + kTile - 1) / kTile;
+    const int nwt = (np + 31) >> 5;
     const int plane_cur = a.scan % a.W;
-    const int tid = threadIdx.x;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int i = tile * kTile + tid;
-        const int cnt = (i < np) ? a.count[i] : 0;
-        int total;
-        const int loc = block_scan_excl(cnt, &total);
-        const int tile_base = a.tile_sum[tile];
-        s_off[tid] = loc;
-        if (tid == 0) s_off[kTile] = total;
-        if (i < np) {
-            a.count[i] = tile_base + loc;  // child offset, read back by tree_off_kernel
-            int t, pos;
-            locate(a, i, t, pos);
-            double x0[4];
-            float P0[16];
-            load_leaf(a, pos, x0, P0);
-            LeafKF kf;
-            leaf_kf<true>(a.model, x0, P0, a.ts.Pd[t], kf);
-            float4 *pb = (float4 *)(a.cur.Pbar + 16 * (size_t)i), *ph = (float4 *)(a.cur.Phat + 16 * (size_t)i);
+    const int warps_per_cta = kTile / 32;
+    for (int wt = blockIdx.x * warps_per_cta + wib; wt < nwt; wt += gridDim.x * warps_per_cta) {
+        const int i = wt * 32 + lane;
+        const int tile = (wt * 32) / kTile;
+        const bool valid = i < np;
+        const int tile_base = a.tile_sum[tile], tile_end = a.tile_sum[tile + 1];
+        const int off_i = valid ? tile_base + a.count[i] : tile_end;
+        const int off_n = (valid && i + 1 < np && ((i + 1) & (kTile - 1))) ? tile_base + a.count[i + 1] : tile_end;
+        const int warp_first = __shfl_sync(0xffffffffu, off_i, 0);
+        const int total = __shfl_sync(0xffffffffu, off_n, 31) - warp_first;
+        const bool staged = total <= kStage;
+        s_off[lane] = off_i - warp_first;
+        if (lane == 0) s_off[32] = total;
+        int t = -1, pos = 0, root_scan = 0;
+        LeafKF kf;
+        if (valid) {
+            const int t_lo = a.tile_tree[tile];
+            const int t_hi = (tile + 1 < ntiles) ? a.tile_tree[tile + 1] : a.T - 1;
+            t = locate_tree(a, i, t_lo, t_hi);
+            pos = a.cur.par_lo[t] + (i - a.cur.par_off[t]);
+            root_scan = a.ts.root_scan[t];
+        }
+        // inherited path planes (entries at or above the tree's root are dropped): issue every load first
+        int rr[MHT_MAX_WINDOW];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                pb[r] = make_float4(kf.Pbar[4 * r], kf.Pbar[4 * r + 1], kf.Pbar[4 * r + 2], kf.Pbar[4 * r + 3]);
-                ph[r] = make_float4(kf.Phat[4 * r], kf.Phat[4 * r + 1], kf.Phat[4 * r + 2], kf.Phat[4 * r + 3]);
-            }
+        for (int w = 0; w < MHT_MAX_WINDOW; ++w) {
+            const int back = ((a.scan - w) % a.W + a.W) % a.W;  // scans since plane w was written
+            const bool take = valid && w < a.W && w != plane_cur && a.scan - back > root_scan;
+            rr[w] = take ? a.rows_prev[(long long)w * a.stride + pos] : -1;
+        }
+        if (valid) {
+            int ent;
+            load_leaf(a, t, pos, kf, ent);
             const double base = a.prev.cnllr[pos];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) s_d[q * kTile + tid] = kf.xbar[q];
-            s_d[4 * kTile + tid] = kf.zhat[0];
-            s_d[5 * kTile + tid] = kf.zhat[1];
+            for (int q = 0; q < 4; ++q) s_d[q * 32 + lane] = kf.xbar[q];
+            s_d[4 * 32 + lane] = kf.zhat[0];
+            s_d[5 * 32 + lane] = kf.zhat[1];
+            s_d[6 * 32 + lane] = base;
+            s_d[7 * 32 + lane] = base + a.ts.miss[t];
+            s_tree[lane] = t;
+            s_ent[lane] = ent;
+            s_pat[lane] = (int)a.prev.pat[pos];
+        }
+        // cluster step (tracker.py:961-974): every measurement on the path links this tree to the other
+        // trees using it; leaves are sorted by path, so a lane repeats its left neighbour's (row, tree)
+        // most of the time and skips the touch
 #pragma unroll
-            for (int q = 0; q < 4; ++q) s_d[(6 + q) * kTile + tid] = kf.si[q];
-            s_d[10 * kTile + tid] = kf.logterm;
-            s_d[11 * kTile + tid] = base + a.ts.miss[t];
-            s_d[12 * kTile + tid] = base;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) s_K[q * kTile + tid] = kf.K[q];
-            s_tree[tid] = t;
-            // inherited path planes (entries at or above the tree's root are dropped)
-            const int root_scan = a.ts.root_scan[t];
-            for (int w = 0; w < a.W; ++w) {
-                const int back = ((a.scan - w) % a.W + a.W) % a.W;  // scans since plane w was written
-                const int s_w = a.scan - back;
-                const int r =
-                    (w != plane_cur && s_w > root_scan) ? a.rows_prev[(long long)w * a.stride + pos] : -1;
-                s_path[w * kTile + tid] = r;
-                // cluster step (tracker.py:961-974): every measurement on the path links this tree to
-                // the other trees using it; all children inherit these rows
-                if (r >= 0) uf_touch_row(a.uf, a.row_owner, a.row_multi, r, t);
+        for (int w = 0; w < MHT_MAX_WINDOW; ++w) {
+            if (w < a.W) {
+                const int r = rr[w];
+                s_path[w * 32 + lane] = r;
+                const int r_up = __shfl_up_sync(0xffffffffu, r, 1), t_up = __shfl_up_sync(0xffffffffu, t, 1);
+                if (r >= 0 && !(lane > 0 && r_up == r && t_up == t)) uf_touch_row(a.uf, a.row_owner, a.row_multi, r, t);
             }
+        }
+        if (valid) {
             int k = 0;
-            int *dst = scratch + tile_base + loc + 1;
+            int *dst = staged ? (s_stage + (off_i - warp_first) + 1) : (scratch + off_i + 1);
             for_each_gated(*a.grid, a.cell_start, a.gz, kf, a.model.eta2,
                            [&](int p, double, double, double) { dst[k++] = a.gidx[p]; });
         }
-        __syncthreads();
-        for (int c = tid; c < total; c += kTile) {
-            int lo = 0, hi = kTile;  // parent = largest p with s_off[p] <= c
-            while (hi - lo > 1) {
+        __syncwarp();
+        for (int c = lane; c < total; c += 32) {
+            int lo = 0, hi = 32;  // parent = largest p with s_off[p] <= c
+#pragma unroll
+            for (int step = 0; step < 5; ++step) {
                 const int mid = (lo + hi) >> 1;
                 if (s_off[mid] <= c) lo = mid; else hi = mid;
             }
             const int p = lo;
             const int k = c - s_off[p];
-            const int first = tile_base + s_off[p];
-            const int t = s_tree[p];
+            const int first = warp_first + s_off[p];
+            const int t_p = s_tree[p];
             int g, row_new, mnum;
             double xo0, xo1, xo2, xo3, cn;
             if (k == 0) {
                 g = first;
                 row_new = -1;
                 mnum = 0;
-                xo0 = s_d[0 * kTile + p];
-                xo1 = s_d[1 * kTile + p];
-                xo2 = s_d[2 * kTile + p];
-                xo3 = s_d[3 * kTile + p];
-                cn = s_d[11 * kTile + p];
+                xo0 = s_d[0 * 32 + p];
+                xo1 = s_d[1 * 32 + p];
+                xo2 = s_d[2 * 32 + p];
+                xo3 = s_d[3 * 32 + p];
+                cn = s_d[7 * 32 + p];
             } else {
                 const int nsib = s_off[p + 1] - s_off[p] - 1;
-                const int m = scratch[first + k];
+                const int *lst = staged ? (s_stage + s_off[p]) : (scratch + first);
+                const int m = lst[k];
                 int rank = 0;
-                for (int q = 1; q <= nsib; ++q) rank += scratch[first + q] < m;
+                for (int q = 1; q <= nsib; ++q) rank += lst[q] < m;
                 g = first + 1 + rank;
                 row_new = plane_cur * a.max_meas + m;
                 mnum = m + 1;
+                const PatGate *e = a.pt_gate + s_ent[p];
+                const float4 sif = __ldg((const float4 *)e->si);
+                const float4 K0 = __ldg((const float4 *)e->K), K1 = __ldg((const float4 *)(e->K + 4));
+                const double logterm = (double)__ldg(&e->logterm);
                 const double2 z = a.z[m];
-                const double v0 = z.x - s_d[4 * kTile + p], v1 = z.y - s_d[5 * kTile + p];
-                const double si[4] = {s_d[6 * kTile + p], s_d[7 * kTile + p], s_d[8 * kTile + p], s_d[9 * kTile + p]};
+                const double v0 = z.x - s_d[4 * 32 + p], v1 = z.y - s_d[5 * 32 + p];
+                const double si[4] = {(double)sif.x, (double)sif.y, (double)sif.z, (double)sif.w};
                 const double d2 = nis_f64(si, v0, v1);
-                xo0 = s_d[0 * kTile + p] + fma((double)s_K[1 * kTile + p], v1, (double)s_K[0 * kTile + p] * v0);
-                xo1 = s_d[1 * kTile + p] + fma((double)s_K[3 * kTile + p], v1, (double)s_K[2 * kTile + p] * v0);
-                xo2 = s_d[2 * kTile + p] + fma((double)s_K[5 * kTile + p], v1, (double)s_K[4 * kTile + p] * v0);
-                xo3 = s_d[3 * kTile + p] + fma((double)s_K[7 * kTile + p], v1, (double)s_K[6 * kTile + p] * v0);
-                cn = s_d[12 * kTile + p] + (0.5 * d2 + s_d[10 * kTile + p]);
-                a.used[m] = 1;
-                uf_touch_row(a.uf, a.row_owner, a.row_multi, row_new, t);
+                xo0 = s_d[0 * 32 + p] + fma((double)K0.y, v1, (double)K0.x * v0);
+                xo1 = s_d[1 * 32 + p] + fma((double)K0.w, v1, (double)K0.z * v0);
+                xo2 = s_d[2 * 32 + p] + fma((double)K1.y, v1, (double)K1.x * v0);
+                xo3 = s_d[3 * 32 + p] + fma((double)K1.w, v1, (double)K1.z * v0);
+                cn = s_d[6 * 32 + p] + (0.5 * d2 + logterm);
+                if (a.used[m] == 0) a.used[m] = 1;
+                uf_touch_row(a.uf, a.row_owner, a.row_multi, row_new, t_p);
             }
             a.cur.xa[g] = make_double2(xo0, xo1);
             a.cur.xb[g] = make_double2(xo2, xo3);
             a.cur.cnllr[g] = cn;
             a.cur.meas[g] = mnum;
-            a.cur.pidx[g] = tile * kTile + p;
-            a.cur.tree[g] = t;
+            a.cur.pidx[g] = wt * 32 + p;
+            a.cur.tree[g] = t_p;
+            a.cur.pat[g] = (unsigned short)(((s_pat[p] << 1) | (k != 0)) & 0xffff);
             for (int w = 0; w < a.W; ++w)
-                a.rows_cur[(long long)w * a.stride + g] = (w == plane_cur) ? row_new : s_path[w * kTile + p];
+                a.rows_cur[(long long)w * a.stride + g] = (w == plane_cur) ? row_new : s_path[w * 32 + p];
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -401,7 +505,7 @@ __global__ void tree_off_kernel(ScanArgs a) {
     const int np = *a.d_np, nc = *a.d_nc;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t <= a.T; t += gridDim.x * blockDim.x) {
         const int po = (t < a.T) ? a.cur.par_off[t] : np;
-        a.cur.tree_off[t] = (po < np) ? a.count[po] : nc;
+        a.cur.tree_off[t] = (po < np) ? a.tile_sum[po / kTile] + a.count[po] : nc;
     }
 }
 
@@ -459,10 +563,11 @@ __global__ void track_update_kernel(UpdateArgs a) {
     a.out.meas[t] = meas;
     a.out.cnllr[t] = cn;
     for (int i = 0; i < 4; ++i) a.out.x[4 * t + i] = x[i];
-    {
-        const float *tab = (meas ? cur.Phat : cur.Pbar) + 16 * (size_t)cur.pidx[sel];
-        for (int i = 0; i < 16; ++i) a.out.P[16 * t + i] = tab[i];
-    }
+    const int root_old = a.ts.root_scan[t];
+    const unsigned pat_sel = cur.pat[sel];
+    const int depth_sel = min(a.scan - root_old, 16);
+    const double Pd_t = a.ts.Pd[t];
+    chain_P(a.model, a.ts.rootP + 16 * t, pat_sel, depth_sel, Pd_t, a.out.P + 16 * t);
     // termination tests, in the reference's order
     double zx = 0.0, zy = 0.0;
     for (int k = 0; k < 4; ++k) {
@@ -480,7 +585,6 @@ __global__ void track_update_kernel(UpdateArgs a) {
         atomicAdd(&a.status->n_dead, 1);
         return;
     }
-    const int root_old = a.ts.root_scan[t];
     const int root_new = max(root_old, a.scan - a.ts.window[t]);
     int lo = cur.tree_off[t], hi = cur.tree_off[t + 1];
     if (root_new > root_old) {
@@ -501,8 +605,14 @@ __global__ void track_update_kernel(UpdateArgs a) {
             a.out.root_x[4 * t] = p01.x; a.out.root_x[4 * t + 1] = p01.y;
             a.out.root_x[4 * t + 2] = p23.x; a.out.root_x[4 * t + 3] = p23.y;
         }
-        const float *tab = (LR.meas[pos] ? LR.Phat : LR.Pbar) + 16 * (size_t)LR.pidx[pos];
-        for (int i = 0; i < 16; ++i) a.out.root_P[16 * t + i] = tab[i];
+        // covariance of the new root: the selected path's first (root_new - root_old) hit/miss bits
+        float Pn[16];
+        chain_P(a.model, a.ts.rootP + 16 * t, pat_sel >> (depth_sel - (root_new - root_old)), root_new - root_old,
+                Pd_t, Pn);
+        for (int i = 0; i < 16; ++i) {
+            a.out.root_P[16 * t + i] = Pn[i];
+            a.ts.rootP[16 * t + i] = Pn[i];
+        }
         // contiguous range of leaves whose path agrees with the selected leaf on (root_old, root_new]
         int l = lo, h = hi;
         while (l < h) {  // lower bound
@@ -528,9 +638,14 @@ __global__ void history_kernel(UpdateArgs a, int t, int pos, int scan_from, doub
     if (threadIdx.x || blockIdx.x) return;
     int n = 0;
     const int root = a.ts.root_scan[t];
+    // covariances along the path: the chain from the root covariance over the leaf's hit/miss bits
+    const unsigned pat_leaf = a.lv[scan_from % a.nslots].pat[pos];
+    const double Pd_t = a.ts.Pd[t];
     for (int s = scan_from; s > root; --s) {
         const Level &L = a.lv[s % a.nslots];
         double *o = out + kHistRec + kHistRec * n++;
+        float Pn[16];
+        chain_P(a.model, a.ts.rootP + 16 * t, pat_leaf >> (scan_from - s), min(s - root, 16), Pd_t, Pn);
         o[0] = (double)L.meas[pos];
         o[1] = L.cnllr[pos];
         {
@@ -538,8 +653,7 @@ __global__ void history_kernel(UpdateArgs a, int t, int pos, int scan_from, doub
             o[2] = p01.x; o[3] = p01.y; o[4] = p23.x; o[5] = p23.y;
         }
         o[6] = (double)s;
-        const float *tab = (L.meas[pos] ? L.Phat : L.Pbar) + 16 * (size_t)L.pidx[pos];
-        for (int i = 0; i < 16; ++i) o[8 + i] = (double)tab[i];
+        for (int i = 0; i < 16; ++i) o[8 + i] = (double)Pn[i];
         pos = L.par_lo[t] + (L.pidx[pos] - L.par_off[t]);
     }
     out[0] = (double)n;
@@ -593,7 +707,7 @@ static void carve_out(char *&p, int T, TrackOut *o) {
 
 static int forest_layout(mht_forest *f, bool commit) {
     const int T = f->cfg.max_trees;
-    const int64_t cn = f->cap_nodes, cp = f->cap_ptab;
+    const int64_t cn = f->cap_nodes;
     char *p = commit ? f->arena : nullptr;
     char *p0 = p;
     for (int s = 0; s < f->nslots; ++s) {
@@ -604,8 +718,7 @@ static int forest_layout(mht_forest *f, bool commit) {
         L.meas = carve<int>(p, cn);
         L.pidx = carve<int>(p, cn);
         L.tree = carve<int>(p, cn);
-        L.Pbar = carve<float>(p, 16 * cp);
-        L.Phat = carve<float>(p, 16 * cp);
+        L.pat = carve<unsigned short>(p, cn);
         L.tree_off = carve<int>(p, T + 1);
         L.par_lo = carve<int>(p, T + 1);
         L.par_off = carve<int>(p, T + 1);
@@ -620,6 +733,10 @@ static int forest_layout(mht_forest *f, bool commit) {
     f->ts.root_cnllr = carve<double>(p, T);
     f->ts.Pd = carve<double>(p, T);
     f->ts.miss = carve<double>(p, T);
+    f->ts.rootP = carve<float>(p, 16 * (int64_t)T);
+    f->pt_gate = carve<PatGate>(p, (int64_t)T * f->PT);
+    f->pt_P = carve<float>(p, 16 * (int64_t)T * f->PT);
+    f->tile_tree = carve<int>(p, f->cap_par / kTile + 4);
     f->out_d_base = p;
     carve_out(p, T, &f->out_d);
     f->out_bytes = p - f->out_d_base;
@@ -676,7 +793,6 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     if (f->T == 0) {  // no trees yet: the scan only advances the clock (tracker.py:207 loops over nothing)
         f->scan = k;
         f->h_level_nodes = 0;
-        f->h_level_ptab = 0;
         f->last_tracks.clear();
         if (info) memset(info, 0, sizeof(*info));
         if (h_used && M) memset(h_used, 0, (size_t)M);
@@ -711,6 +827,11 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     a.z = (const double2 *)d_z;
     a.count = f->count;
     a.tile_sum = f->tile_sum;
+    a.tile_tree = f->tile_tree;
+    a.pt_gate = f->pt_gate;
+    a.pt_P = f->pt_P;
+    a.PT = f->PT;
+    a.N = f->cfg.n_scan_window;
     a.d_np = f->d_np;
     a.d_nc = f->d_nc;
     a.used = f->used_d;
@@ -744,6 +865,7 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     if (int rc = assoc_begin(c, f->aw, grid_dim, s, k > 1)) return rc;
     MHT_CUDA(cudaMemsetAsync(f->used_d, 0, (size_t)(M ? M : 1), s));
     live_scan_kernel<<<1, 1024, 0, s>>>(a);
+    pat_table_kernel<<<f->T, 128, 0, s>>>(a);
     if (int rc = launch_grid_build(d_z, (int)M, grid, cell_start, cell_fill, gz, gidx, s)) return rc;
     forest_count_kernel<<<grid_dim, kTile, 0, s>>>(a);
     forest_scan_tiles_kernel<<<1, 1024, 0, s>>>(a);
@@ -804,7 +926,6 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
         }
     }
     f->h_level_nodes = st.n_children;
-    f->h_level_ptab = st.n_parents;
     if (info) {
         memset(info, 0, sizeof(*info));
         info->n_parents = st.n_parents;
@@ -852,7 +973,7 @@ extern "C" int mht_forest_create(const mht_forest_config *cfg, mht_forest **out)
     f->scan = 0;
     f->cap_nodes = cfg->max_nodes;
     f->cap_par = cfg->max_parents;
-    f->cap_ptab = cfg->max_parents + cfg->max_trees;
+    f->PT = 1 << (cfg->n_scan_window + 1);
     f->arena = nullptr;
     forest_layout(f, false);
     if (cudaMalloc(&f->arena, (size_t)f->bytes) != cudaSuccess) {
@@ -890,7 +1011,6 @@ extern "C" int mht_forest_create(const mht_forest_config *cfg, mht_forest **out)
     f->h_last_pos.assign(T, -1);
     f->trunk.resize(T);
     f->h_level_nodes = 0;
-    f->h_level_ptab = 0;
     *out = f;
     return MHT_OK;
 }
@@ -916,14 +1036,15 @@ extern "C" int mht_forest_initiate(mht_forest *f, const double x0[4], const floa
         set_error("mht_forest_initiate: invalid argument");
         return MHT_E_INVALID;
     }
-    if (f->T >= f->cfg.max_trees || f->h_level_nodes >= f->cap_nodes || f->h_level_ptab >= f->cap_ptab) {
+    if (f->T >= f->cfg.max_trees || f->h_level_nodes >= f->cap_nodes) {
         set_error("mht_forest_initiate: capacity exceeded (trees %d/%d)", f->T, f->cfg.max_trees);
         return MHT_E_CAPACITY;
     }
     cudaStream_t s = f->stream;
     const int t = f->T;
     const Level &L = f->lv[f->scan % f->nslots];
-    const int pos = (int)f->h_level_nodes, pi = (int)f->h_level_ptab;
+    const int pos = (int)f->h_level_nodes, pi = 0;
+    const unsigned short pat0 = 0;
     const int zero = 0, one = 1, scan = f->scan, win = f->cfg.n_scan_window, hi = pos + 1;
     const double cn = 0.0, miss = -log(1.0 - Pd);
     int minus[MHT_MAX_WINDOW];
@@ -934,7 +1055,8 @@ extern "C" int mht_forest_initiate(mht_forest *f, const double x0[4], const floa
     MHT_CUDA(cudaMemcpyAsync(L.meas + pos, &zero, 4, cudaMemcpyHostToDevice, s));
     MHT_CUDA(cudaMemcpyAsync(L.pidx + pos, &pi, 4, cudaMemcpyHostToDevice, s));
     MHT_CUDA(cudaMemcpyAsync(L.tree + pos, &t, 4, cudaMemcpyHostToDevice, s));
-    MHT_CUDA(cudaMemcpyAsync(L.Pbar + 16 * (size_t)pi, P0, 64, cudaMemcpyHostToDevice, s));
+    MHT_CUDA(cudaMemcpyAsync(L.pat + pos, &pat0, 2, cudaMemcpyHostToDevice, s));
+    MHT_CUDA(cudaMemcpyAsync(f->ts.rootP + 16 * (size_t)t, P0, 64, cudaMemcpyHostToDevice, s));
     for (int w = 0; w < f->W; ++w)
         MHT_CUDA(cudaMemcpyAsync(f->rows[f->scan & 1] + (int64_t)w * f->cap_nodes + pos, minus, 4,
                                  cudaMemcpyHostToDevice, s));
@@ -949,7 +1071,6 @@ extern "C" int mht_forest_initiate(mht_forest *f, const double x0[4], const floa
     MHT_CUDA(cudaMemcpyAsync(f->ts.miss + t, &miss, 8, cudaMemcpyHostToDevice, s));
     MHT_CUDA(cudaStreamSynchronize(s));
     f->h_level_nodes += 1;
-    f->h_level_ptab += 1;
     f->h_alive[t] = 1;
     f->h_root_scan[t] = f->h_init_scan[t] = f->scan;
     f->h_last_pos[t] = pos;
