@@ -96,7 +96,9 @@ __device__ __forceinline__ void uf_union(int *uf, int a, int b) {
         if (atomicCAS(&uf[b], b, a) == b) return;
     }
 }
-// tree t uses measurement row r: first toucher owns the row, later trees are united with the owner
+// tree t uses measurement row r: first toucher owns the row, later trees are united with the owner.
+// Fast path: equal (possibly stale, L1-cached) parent pointers prove t and o are already in one set --
+// parents only ever move to other members of the same set -- so the volatile find chains are skipped.
 __device__ __forceinline__ void uf_touch_row(int *uf, int *row_owner, int *row_multi, int r, int t) {
     int o = row_owner[r];
     if (o < 0) {
@@ -104,8 +106,8 @@ __device__ __forceinline__ void uf_touch_row(int *uf, int *row_owner, int *row_m
         if (o < 0) o = t;
     }
     if (o != t) {
-        row_multi[r] = 1;
-        uf_union(uf, t, o);
+        if (row_multi[r] == 0) row_multi[r] = 1;
+        if (uf[t] != uf[o]) uf_union(uf, t, o);
     }
 }
 

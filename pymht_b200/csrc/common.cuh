@@ -158,11 +158,12 @@ __device__ __forceinline__ void filter_f64(const LeafKF &kf, double v0, double v
     for (int i = 0; i < 4; ++i) xh[i] = kf.xbar[i] + fma((double)kf.K[i * 2 + 1], v1, (double)kf.K[i * 2] * v0);
 }
 
-// Visit every measurement of the grid inside the leaf's gate.  f(sorted_position, d2, v0, v1).
+// Visit every measurement of the grid inside the leaf's gate.  f(original measurement index, d2, v0, v1).
+// The index travels with the point (loaded before the gate test, not after it).
 template <class F>
 __device__ __forceinline__ void for_each_gated(const GridDesc &g, const int *__restrict__ cell_start,
-                                               const double2 *__restrict__ gz, const LeafKF &kf, double eta2,
-                                               F f) {
+                                               const double2 *__restrict__ gz, const int *__restrict__ gidx,
+                                               const LeafKF &kf, double eta2, F f) {
     if (g.n_meas == 0) return;
     int cx0 = (int)floor((kf.zhat[0] - kf.hx - g.x0) * g.inv_cell);
     int cx1 = (int)floor((kf.zhat[0] + kf.hx - g.x0) * g.inv_cell);
@@ -177,9 +178,10 @@ __device__ __forceinline__ void for_each_gated(const GridDesc &g, const int *__r
         const int end = cell_start[cy * g.nx + cx1 + 1];  // cells of one row are contiguous
         for (int p = beg; p < end; ++p) {
             const double2 z = gz[p];
+            const int m = gidx[p];
             const double v0 = z.x - kf.zhat[0], v1 = z.y - kf.zhat[1];
             const double d2 = nis_f64(kf.si, v0, v1);
-            if (d2 <= eta2) f(p, d2, v0, v1);
+            if (d2 <= eta2) f(m, d2, v0, v1);
         }
     }
 }

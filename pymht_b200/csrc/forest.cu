@@ -85,6 +85,7 @@ struct mht_forest {
     PatGate *pt_gate;          // [max_trees][PT]
     float *pt_P;               // [max_trees][PT][16] posterior covariance per pattern
     int *tile_tree;            // [cap_par/kTile + 4] tree of the first live leaf of every tile
+    int *glist;                // [cap_par][kInline] inline gated lists
     int64_t bytes;
     char *arena;
     Level lv[MHT_MAX_WINDOW + 2];
@@ -130,6 +131,7 @@ struct ScanArgs {
     const int *gidx;
     const double2 *z;
     int *count, *tile_sum, *tile_tree;
+    int *glist;           // [cap_par][kInline] ascending gated measurement indices per live leaf
     int *d_np, *d_nc;
     PatGate *pt_gate;
     float *pt_P;
@@ -286,8 +288,12 @@ __device__ __forceinline__ int block_scan_excl(int v, int *total) {
     return excl;
 }
 
-// pass 1: children per live leaf (1 miss + gated): tile-local exclusive offsets + per-tile sums
-__global__ void __launch_bounds__(kTile) forest_count_kernel(ScanArgs a) {
+// pass 1 -- the gate proper: children per live leaf (1 miss + gated) as tile-local exclusive offsets +
+// per-tile sums, and the leaf's gated measurement indices, ASCENDING, in an inline list of kInline slots
+// (sorted insertion through a min/max chain in registers).  Leaves with more gated measurements than
+// slots are re-gated by pass 2.
+constexpr int kInline = 8;
+__global__ void __launch_bounds__(kTile, 4) forest_count_kernel(ScanArgs a) {
     if (a.status->overflow) return;
     const int np = *a.d_np;
     const int ntiles = (np + kTile - 1) / kTile;
@@ -303,9 +309,24 @@ __global__ void __launch_bounds__(kTile) forest_count_kernel(ScanArgs a) {
             LeafKF kf;
             int ent;
             load_leaf(a, t, pos, kf, ent);
+            int lst[kInline];
+#pragma unroll
+            for (int q = 0; q < kInline; ++q) lst[q] = 0x7fffffff;
             cnt = 1;
-            for_each_gated(*a.grid, a.cell_start, a.gz, kf, a.model.eta2,
-                           [&](int, double, double, double) { ++cnt; });
+            for_each_gated(*a.grid, a.cell_start, a.gz, a.gidx, kf, a.model.eta2,
+                           [&](int m, double, double, double) {
+                               ++cnt;
+                               int v = m;
+#pragma unroll
+                               for (int q = 0; q < kInline; ++q) {
+                                   const int lo = min(lst[q], v);
+                                   v = max(lst[q], v);
+                                   lst[q] = lo;
+                               }
+                           });
+            int4 *dst = (int4 *)(a.glist + (size_t)kInline * i);
+            dst[0] = make_int4(lst[0], lst[1], lst[2], lst[3]);
+            dst[1] = make_int4(lst[4], lst[5], lst[6], lst[7]);
         }
         int total;
         const int excl = block_scan_excl(cnt, &total);
@@ -348,18 +369,18 @@ __global__ void __launch_bounds__(1024, 1) forest_scan_tiles_kernel(ScanArgs a) 
 // pass 2: write the new level.  Child order per leaf = [miss, gated by ascending measurement index]
 // (Target.spawnNewNodes, pyTarget.py:239-254).  Every WARP owns 32 consecutive live leaves and never
 // synchronises with the rest of its CTA (child offsets come from pass 1):
-//   phase A (lane = leaf): state prediction, pattern-table entry, inherited path planes, cluster links,
-//            gated measurement indices (grid order) -> warp staging (shared memory; HBM scratch if the
-//            warp has more than kStage children);
-//   phase B (lane = CHILD, consecutive lanes = consecutive children): rank the measurement among its
-//            siblings (ascending index), filter, score, and store every field coalesced.
-constexpr int kStage = 384;  // staged child slots per warp
+//   phase A (lane = leaf): state prediction, pattern-table entry, inherited path planes, cluster links
+//            (and, for the rare leaf with more than kInline gated measurements, the gate again, unsorted
+//            into HBM scratch);
+//   phase B (lane = CHILD, consecutive lanes = consecutive children): measurement from the parent's inline
+//            list, filter, score, and every field stored coalesced.
 constexpr int kEmitD = 8;    // doubles per leaf in smem: xbar[4] zhat[2] base_cnllr miss_cnllr
 __host__ __device__ inline size_t emit_warp_bytes(int W) {
-    return (size_t)32 * kEmitD * 8 + (size_t)(3 + W) * 32 * 4 + 36 * 4 + kStage * 4;
+    return (size_t)32 * kEmitD * 8 + (size_t)(3 + W) * 32 * 4 + 36 * 4;
 }
 __host__ __device__ inline size_t emit_smem_bytes(int W) { return (kTile / 32) * emit_warp_bytes(W); }
 
+template <int WMAX>
 __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, int *scratch) {
     if (a.status->overflow) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -370,12 +391,12 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, int *scr
     int *s_ent = s_tree + 32;                  // [32] pattern-table entry
     int *s_pat = s_ent + 32;                   // [32] hit/miss history of the leaf
     int *s_off = s_pat + 32;                   // [33] child offsets inside the warp (+3 pad)
-    int *s_stage = s_off + 36;                 // [kStage]
-    int *s_path = s_stage + kStage;            // [W][32]
+    int *s_path = s_off + 36;                  // [W][32]
     const int np = *a.d_np;
     const int ntiles = (np + kTile - 1) / kTile;
     const int nwt = (np + 31) >> 5;
-    const int plane_cur = a.scan % a.W;
+    const int W = a.W;
+    const int plane_cur = a.scan % W;
     const int warps_per_cta = kTile / 32;
     for (int wt = blockIdx.x * warps_per_cta + wib; wt < nwt; wt += gridDim.x * warps_per_cta) {
         const int i = wt * 32 + lane;
@@ -386,11 +407,9 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, int *scr
         const int off_n = (valid && i + 1 < np && ((i + 1) & (kTile - 1))) ? tile_base + a.count[i + 1] : tile_end;
         const int warp_first = __shfl_sync(0xffffffffu, off_i, 0);
         const int total = __shfl_sync(0xffffffffu, off_n, 31) - warp_first;
-        const bool staged = total <= kStage;
         s_off[lane] = off_i - warp_first;
         if (lane == 0) s_off[32] = total;
-        int t = -1, pos = 0, root_scan = 0;
-        LeafKF kf;
+        int t = -1, pos = 0, root_scan = 0x7fffffff;
         if (valid) {
             const int t_lo = a.tile_tree[tile];
             const int t_hi = (tile + 1 < ntiles) ? a.tile_tree[tile + 1] : a.T - 1;
@@ -398,15 +417,18 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, int *scr
             pos = a.cur.par_lo[t] + (i - a.cur.par_off[t]);
             root_scan = a.ts.root_scan[t];
         }
-        // inherited path planes (entries at or above the tree's root are dropped): issue every load first
-        int rr[MHT_MAX_WINDOW];
+        // inherited path planes (entries at or above the tree's root are dropped): every load is issued
+        // before the first use.  Plane w holds the rows of scan  a.scan - ((a.scan - w) mod W).
+        int rr[WMAX];
 #pragma unroll
-        for (int w = 0; w < MHT_MAX_WINDOW; ++w) {
-            const int back = ((a.scan - w) % a.W + a.W) % a.W;  // scans since plane w was written
-            const bool take = valid && w < a.W && w != plane_cur && a.scan - back > root_scan;
+        for (int w = 0; w < WMAX; ++w) {
+            int back = plane_cur - w;        // (a.scan - w) mod W, given plane_cur = a.scan mod W
+            back += back < 0 ? W : 0;
+            const bool take = w < W && back != 0 && a.scan - back > root_scan;
             rr[w] = take ? a.rows_prev[(long long)w * a.stride + pos] : -1;
         }
         if (valid) {
+            LeafKF kf;
             int ent;
             load_leaf(a, t, pos, kf, ent);
             const double base = a.prev.cnllr[pos];
@@ -419,27 +441,29 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, int *scr
             s_tree[lane] = t;
             s_ent[lane] = ent;
             s_pat[lane] = (int)a.prev.pat[pos];
+            if (off_n - off_i - 1 > kInline) {  // rare: gate again, unsorted, into the leaf's scratch run
+                int k = 0;
+                int *dst = scratch + off_i + 1;
+                for_each_gated(*a.grid, a.cell_start, a.gz, a.gidx, kf, a.model.eta2,
+                               [&](int m, double, double, double) { dst[k++] = m; });
+            }
         }
         // cluster step (tracker.py:961-974): every measurement on the path links this tree to the other
         // trees using it; leaves are sorted by path, so a lane repeats its left neighbour's (row, tree)
         // most of the time and skips the touch
 #pragma unroll
-        for (int w = 0; w < MHT_MAX_WINDOW; ++w) {
-            if (w < a.W) {
+        for (int w = 0; w < WMAX; ++w) {
+            if (w < W) {
                 const int r = rr[w];
                 s_path[w * 32 + lane] = r;
                 const int r_up = __shfl_up_sync(0xffffffffu, r, 1), t_up = __shfl_up_sync(0xffffffffu, t, 1);
                 if (r >= 0 && !(lane > 0 && r_up == r && t_up == t)) uf_touch_row(a.uf, a.row_owner, a.row_multi, r, t);
             }
         }
-        if (valid) {
-            int k = 0;
-            int *dst = staged ? (s_stage + (off_i - warp_first) + 1) : (scratch + off_i + 1);
-            for_each_gated(*a.grid, a.cell_start, a.gz, kf, a.model.eta2,
-                           [&](int p, double, double, double) { dst[k++] = a.gidx[p]; });
-        }
         __syncwarp();
-        for (int c = lane; c < total; c += 32) {
+        for (int c0 = 0; c0 < total; c0 += 32) {
+            const int c = c0 + lane;
+            const bool live = c < total;
             int lo = 0, hi = 32;  // parent = largest p with s_off[p] <= c
 #pragma unroll
             for (int step = 0; step < 5; ++step) {
@@ -447,29 +471,37 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, int *scr
                 if (s_off[mid] <= c) lo = mid; else hi = mid;
             }
             const int p = lo;
-            const int k = c - s_off[p];
+            const int k = live ? c - s_off[p] : 0;
             const int first = warp_first + s_off[p];
             const int t_p = s_tree[p];
-            int g, row_new, mnum;
-            double xo0, xo1, xo2, xo3, cn;
-            if (k == 0) {
-                g = first;
-                row_new = -1;
-                mnum = 0;
-                xo0 = s_d[0 * 32 + p];
-                xo1 = s_d[1 * 32 + p];
-                xo2 = s_d[2 * 32 + p];
-                xo3 = s_d[3 * 32 + p];
-                cn = s_d[7 * 32 + p];
-            } else {
+            const int ip = wt * 32 + p;      // live index of the parent
+            int g = first, row_new = -1, m = -1;
+            if (live && k > 0) {
                 const int nsib = s_off[p + 1] - s_off[p] - 1;
-                const int *lst = staged ? (s_stage + s_off[p]) : (scratch + first);
-                const int m = lst[k];
-                int rank = 0;
-                for (int q = 1; q <= nsib; ++q) rank += lst[q] < m;
-                g = first + 1 + rank;
+                if (nsib <= kInline) {
+                    m = a.glist[(size_t)kInline * ip + (k - 1)];
+                    g = first + k;
+                } else {
+                    const int *lst = scratch + first;
+                    m = lst[k];
+                    int rank = 0;
+                    for (int q = 1; q <= nsib; ++q) rank += lst[q] < m;
+                    g = first + 1 + rank;
+                }
                 row_new = plane_cur * a.max_meas + m;
-                mnum = m + 1;
+            }
+            // one lane per distinct (tree, new row) of this batch marks the measurement used and links
+            // the tree to the row's other users
+            const long long key = m >= 0 ? (((long long)t_p << 32) | (unsigned)row_new) : (long long)(-1 - lane);
+            const unsigned grp = __match_any_sync(0xffffffffu, key);
+            if (m >= 0 && (int)(__ffs(grp) - 1) == lane) {
+                if (a.used[m] == 0) a.used[m] = 1;
+                uf_touch_row(a.uf, a.row_owner, a.row_multi, row_new, t_p);
+            }
+            if (!live) continue;
+            double xo0 = s_d[0 * 32 + p], xo1 = s_d[1 * 32 + p], xo2 = s_d[2 * 32 + p], xo3 = s_d[3 * 32 + p];
+            double cn = s_d[7 * 32 + p];
+            if (m >= 0) {
                 const PatGate *e = a.pt_gate + s_ent[p];
                 const float4 sif = __ldg((const float4 *)e->si);
                 const float4 K0 = __ldg((const float4 *)e->K), K1 = __ldg((const float4 *)(e->K + 4));
@@ -478,23 +510,22 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, int *scr
                 const double v0 = z.x - s_d[4 * 32 + p], v1 = z.y - s_d[5 * 32 + p];
                 const double si[4] = {(double)sif.x, (double)sif.y, (double)sif.z, (double)sif.w};
                 const double d2 = nis_f64(si, v0, v1);
-                xo0 = s_d[0 * 32 + p] + fma((double)K0.y, v1, (double)K0.x * v0);
-                xo1 = s_d[1 * 32 + p] + fma((double)K0.w, v1, (double)K0.z * v0);
-                xo2 = s_d[2 * 32 + p] + fma((double)K1.y, v1, (double)K1.x * v0);
-                xo3 = s_d[3 * 32 + p] + fma((double)K1.w, v1, (double)K1.z * v0);
+                xo0 = xo0 + fma((double)K0.y, v1, (double)K0.x * v0);
+                xo1 = xo1 + fma((double)K0.w, v1, (double)K0.z * v0);
+                xo2 = xo2 + fma((double)K1.y, v1, (double)K1.x * v0);
+                xo3 = xo3 + fma((double)K1.w, v1, (double)K1.z * v0);
                 cn = s_d[6 * 32 + p] + (0.5 * d2 + logterm);
-                if (a.used[m] == 0) a.used[m] = 1;
-                uf_touch_row(a.uf, a.row_owner, a.row_multi, row_new, t_p);
             }
             a.cur.xa[g] = make_double2(xo0, xo1);
             a.cur.xb[g] = make_double2(xo2, xo3);
             a.cur.cnllr[g] = cn;
-            a.cur.meas[g] = mnum;
-            a.cur.pidx[g] = wt * 32 + p;
+            a.cur.meas[g] = m + 1;
+            a.cur.pidx[g] = ip;
             a.cur.tree[g] = t_p;
-            a.cur.pat[g] = (unsigned short)(((s_pat[p] << 1) | (k != 0)) & 0xffff);
-            for (int w = 0; w < a.W; ++w)
-                a.rows_cur[(long long)w * a.stride + g] = (w == plane_cur) ? row_new : s_path[w * 32 + p];
+            a.cur.pat[g] = (unsigned short)(((s_pat[p] << 1) | (m >= 0)) & 0xffff);
+#pragma unroll
+            for (int w = 0; w < WMAX; ++w)
+                if (w < W) a.rows_cur[(long long)w * a.stride + g] = (w == plane_cur) ? row_new : s_path[w * 32 + p];
         }
         __syncwarp();
     }
@@ -737,6 +768,7 @@ static int forest_layout(mht_forest *f, bool commit) {
     f->pt_gate = carve<PatGate>(p, (int64_t)T * f->PT);
     f->pt_P = carve<float>(p, 16 * (int64_t)T * f->PT);
     f->tile_tree = carve<int>(p, f->cap_par / kTile + 4);
+    f->glist = carve<int>(p, 8 * (f->cap_par + 1));
     f->out_d_base = p;
     carve_out(p, T, &f->out_d);
     f->out_bytes = p - f->out_d_base;
@@ -828,6 +860,7 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     a.count = f->count;
     a.tile_sum = f->tile_sum;
     a.tile_tree = f->tile_tree;
+    a.glist = f->glist;
     a.pt_gate = f->pt_gate;
     a.pt_P = f->pt_P;
     a.PT = f->PT;
@@ -869,7 +902,8 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     if (int rc = launch_grid_build(d_z, (int)M, grid, cell_start, cell_fill, gz, gidx, s)) return rc;
     forest_count_kernel<<<grid_dim, kTile, 0, s>>>(a);
     forest_scan_tiles_kernel<<<1, 1024, 0, s>>>(a);
-    forest_emit_kernel<<<grid_dim, kTile, emit_smem_bytes(f->W), s>>>(a, (int *)f->aw.rc);
+    if (f->W <= 8) forest_emit_kernel<8><<<grid_dim, kTile, emit_smem_bytes(f->W), s>>>(a, (int *)f->aw.rc);
+    else forest_emit_kernel<MHT_MAX_WINDOW><<<grid_dim, kTile, emit_smem_bytes(f->W), s>>>(a, (int *)f->aw.rc);
     tree_off_kernel<<<(f->T + 256) / 256, 256, 0, s>>>(a);
     MHT_CUDA(cudaGetLastError());
     MHT_CUDA(cudaEventRecord(f->ev[1], s));
@@ -992,7 +1026,10 @@ extern "C" int mht_forest_create(const mht_forest_config *cfg, mht_forest **out)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&f->ev[i]);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(forest_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        e = cudaFuncSetAttribute(forest_emit_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)emit_smem_bytes(8));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(forest_emit_kernel<MHT_MAX_WINDOW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)emit_smem_bytes(MHT_MAX_WINDOW));
     if (e == cudaSuccess) e = cudaMemsetAsync(f->ts.alive, 0, sizeof(int) * T, f->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(f->rows[0], 0xff, sizeof(int) * (size_t)f->W * f->cap_nodes, f->stream);

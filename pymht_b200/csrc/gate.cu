@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kTile) gate_batch_count_kernel(GateBatchArgs a
             load_leaf(a, i, x0, P0);
             LeafKF kf;
             leaf_kf<false>(a.model, x0, P0, a.Pd[i], kf);
-            for_each_gated(*a.grid, a.cell_start, a.gz, kf, a.model.eta2,
+            for_each_gated(*a.grid, a.cell_start, a.gz, a.gidx, kf, a.model.eta2,
                            [&](int, double, double, double) { ++cnt; });
             a.count[i] = cnt;
         }
@@ -300,8 +300,8 @@ __global__ void __launch_bounds__(kTile) gate_batch_emit_kernel(GateBatchArgs a)
             a.miss_cnllr[i] = base - log(1.0 - Pd);
             if ((long long)off + cnt <= a.cap) {
                 int k = 0;
-                for_each_gated(*a.grid, a.cell_start, a.gz, kf, a.model.eta2,
-                               [&](int p, double, double, double) { a.pair_meas[off + (k++)] = a.gidx[p]; });
+                for_each_gated(*a.grid, a.cell_start, a.gz, a.gidx, kf, a.model.eta2,
+                               [&](int m, double, double, double) { a.pair_meas[off + (k++)] = m; });
                 sort_run(a.pair_meas + off, cnt);
                 for (k = 0; k < cnt; ++k) {
                     const int m = a.pair_meas[off + k];
