@@ -313,12 +313,12 @@ def exchange(dist, device, t_dev, t_e2e, n_tracks):
 
 def launches_per_scan(d):
     """Kernel launches of libmht_b200 per scan, counted from the launch sequence in csrc/forest.cu and
-    csrc/assoc.cu: gate 7 (live_scan, pat_table, grid_build, count, scan_tiles, emit, tree_off) + assoc reset 1 +
+    csrc/assoc.cu: gate 9 (live_scan, pat_table, grid_build, gate, gate_heavy, count_scan, scan_tiles, emit, tree_off) + assoc reset 1 +
     cluster bookkeeping 5 + settle pass 7 + dual loop (ONE persistent cooperative kernel per round; with
     sifting 3 rounds, each preceded by a pricing pass, 3 active-list kernels and a reset, plus 2 re-arms)
     + final bound/candidates/repair 11 + track update 1."""
     sift = d["n_children"] > 1000000
-    return 7 + 1 + 5 + 7 + (3 * 6 + 2 if sift else 1) + 11 + 1
+    return 9 + 1 + 5 + 7 + (3 * 6 + 2 if sift else 1) + 11 + 1
 
 
 if __name__ == "__main__":

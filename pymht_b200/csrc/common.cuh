@@ -158,21 +158,27 @@ __device__ __forceinline__ void filter_f64(const LeafKF &kf, double v0, double v
     for (int i = 0; i < 4; ++i) xh[i] = kf.xbar[i] + fma((double)kf.K[i * 2 + 1], v1, (double)kf.K[i * 2] * v0);
 }
 
-// Visit every measurement of the grid inside the leaf's gate.  f(original measurement index, d2, v0, v1).
-// The index travels with the point (loaded before the gate test, not after it).
-template <class F>
-__device__ __forceinline__ void for_each_gated(const GridDesc &g, const int *__restrict__ cell_start,
-                                               const double2 *__restrict__ gz, const int *__restrict__ gidx,
-                                               const LeafKF &kf, double eta2, F f) {
-    if (g.n_meas == 0) return;
-    int cx0 = (int)floor((kf.zhat[0] - kf.hx - g.x0) * g.inv_cell);
-    int cx1 = (int)floor((kf.zhat[0] + kf.hx - g.x0) * g.inv_cell);
-    int cy0 = (int)floor((kf.zhat[1] - kf.hy - g.y0) * g.inv_cell);
-    int cy1 = (int)floor((kf.zhat[1] + kf.hy - g.y0) * g.inv_cell);
+// Grid cells under the bounding box of the leaf's gate ellipse; false = nothing to visit.
+__device__ __forceinline__ bool gate_box(const GridDesc &g, const LeafKF &kf, int &cx0, int &cx1, int &cy0, int &cy1) {
+    if (g.n_meas == 0) return false;
+    cx0 = (int)floor((kf.zhat[0] - kf.hx - g.x0) * g.inv_cell);
+    cx1 = (int)floor((kf.zhat[0] + kf.hx - g.x0) * g.inv_cell);
+    cy0 = (int)floor((kf.zhat[1] - kf.hy - g.y0) * g.inv_cell);
+    cy1 = (int)floor((kf.zhat[1] + kf.hy - g.y0) * g.inv_cell);
     cx0 = max(cx0, 0);
     cy0 = max(cy0, 0);
     cx1 = min(cx1, g.nx - 1);
     cy1 = min(cy1, g.ny - 1);
+    return cx0 <= cx1 && cy0 <= cy1;
+}
+
+// Visit every measurement inside the leaf's gate among the cells [cx0,cx1] x [cy0,cy1].
+// f(original measurement index, d2, v0, v1); the index travels with the point (loaded before the test).
+template <class F>
+__device__ __forceinline__ void for_each_gated_box(const GridDesc &g, const int *__restrict__ cell_start,
+                                                   const double2 *__restrict__ gz, const int *__restrict__ gidx,
+                                                   const LeafKF &kf, double eta2, int cx0, int cx1, int cy0, int cy1,
+                                                   F f) {
     for (int cy = cy0; cy <= cy1; ++cy) {
         const int beg = cell_start[cy * g.nx + cx0];
         const int end = cell_start[cy * g.nx + cx1 + 1];  // cells of one row are contiguous
@@ -184,6 +190,15 @@ __device__ __forceinline__ void for_each_gated(const GridDesc &g, const int *__r
             if (d2 <= eta2) f(m, d2, v0, v1);
         }
     }
+}
+
+template <class F>
+__device__ __forceinline__ void for_each_gated(const GridDesc &g, const int *__restrict__ cell_start,
+                                               const double2 *__restrict__ gz, const int *__restrict__ gidx,
+                                               const LeafKF &kf, double eta2, F f) {
+    int cx0, cx1, cy0, cy1;
+    if (!gate_box(g, kf, cx0, cx1, cy0, cy1)) return;
+    for_each_gated_box(g, cell_start, gz, gidx, kf, eta2, cx0, cx1, cy0, cy1, f);
 }
 
 // ordered-uint64 encoding of a double for atomicMin/Max

@@ -86,6 +86,9 @@ struct mht_forest {
     float *pt_P;               // [max_trees][PT][16] posterior covariance per pattern
     int *tile_tree;            // [cap_par/kTile + 4] tree of the first live leaf of every tile
     int *glist;                // [cap_par][kInline] inline gated lists
+    int2 *heavy_list;          // [cap_par]
+    unsigned *tm_bits;         // [max_trees][tm_words]
+    int tm_words;
     int64_t bytes;
     char *arena;
     Level lv[MHT_MAX_WINDOW + 2];
@@ -132,6 +135,12 @@ struct ScanArgs {
     const double2 *z;
     int *count, *tile_sum, *tile_tree;
     int *glist;           // [cap_par][kInline] ascending gated measurement indices per live leaf
+    int2 *heavy_list;            // worklist (live index, tree) of leaves gated by the warp-per-leaf kernel
+    int *heavy_n;
+    int heavy_rows, heavy_cand;  // thresholds: grid rows / candidate measurements under the gate box
+    unsigned *tm_bits;           // [max_trees][tm_words] (tree, measurement) pairs already linked this scan
+    int tm_words;
+    long long *pool_ctr;
     int *d_np, *d_nc;
     PatGate *pt_gate;
     float *pt_P;
@@ -160,6 +169,8 @@ __global__ void __launch_bounds__(1024, 1) live_scan_kernel(ScanArgs a) {
             acc += v;
         }
         *a.d_np = acc;
+        *a.heavy_n = 0;
+        *a.pool_ctr = 0;
         a.status->n_parents = acc;
         a.status->overflow = acc > a.cap_par ? 1 : 0;
         a.status->n_dead = 0;
@@ -172,8 +183,12 @@ __global__ void __launch_bounds__(1024, 1) live_scan_kernel(ScanArgs a) {
     for (int t = lo; t < hi; ++t) {
         a.cur.par_off[t] = acc;
         a.cur.par_lo[t] = a.ts.live_lo[t];
-        acc += a.ts.alive[t] ? a.ts.live_hi[t] - a.ts.live_lo[t] : 0;
+        const int len = a.ts.alive[t] ? a.ts.live_hi[t] - a.ts.live_lo[t] : 0;
+        // tiles whose first live leaf belongs to this tree (the gate kernels start their tree search here)
+        for (int k = (acc + kTile - 1) / kTile; (long long)k * kTile < (long long)acc + len; ++k) a.tile_tree[k] = t;
+        acc += len;
     }
+    if (threadIdx.x == 0) a.tile_tree[(*a.d_np + kTile - 1) / kTile] = T - 1;   // sentinel for the last tile
 }
 
 // live index -> (tree, position in the previous level): largest t in [t_lo, t_hi] with par_off[t] <= i.
@@ -288,53 +303,219 @@ __device__ __forceinline__ int block_scan_excl(int v, int *total) {
     return excl;
 }
 
-// pass 1 -- the gate proper: children per live leaf (1 miss + gated) as tile-local exclusive offsets +
-// per-tile sums, and the leaf's gated measurement indices, ASCENDING, in an inline list of kInline slots
-// (sorted insertion through a min/max chain in registers).  Leaves with more gated measurements than
-// slots are re-gated by pass 2.
-constexpr int kInline = 8;
-__global__ void __launch_bounds__(kTile, 4) forest_count_kernel(ScanArgs a) {
+// Bitonic sorting network on registers (compile-time indices only).
+template <int N>
+__device__ __forceinline__ void sort_net(int (&r)[N]) {
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1)
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const int x = r[i], y = r[l];
+                    r[i] = up ? min(x, y) : max(x, y);
+                    r[l] = up ? max(x, y) : min(x, y);
+                }
+            }
+}
+
+// tree t gates measurement m this scan: mark the measurement used and link the tree to the row's other
+// users (tracker.py:331-332, :961-974) -- once per (tree, measurement): a bitmap filters the repeats
+// (thousands of leaves of a tree gate the same measurement).
+__device__ __forceinline__ void link_new_row(const ScanArgs &a, int plane_cur, int t, int m);
+
+// pass 1 -- the gate proper, one thread per live leaf: children of the leaf (1 miss + gated) and its
+// gated measurement indices, ASCENDING, in an inline list of kInline slots (collected in shared memory,
+// sorted by a register network).  Leaves whose gate box holds very many candidate measurements (several
+// recent misses blow the gate up) or more than kInline gated ones would make their whole warp wait: they
+// go to a worklist for the warp-per-leaf kernel below.  The cluster links of the new measurement rows
+// are made here, from registers.
+constexpr int kInline = 16;
+__global__ void __launch_bounds__(kTile, 4) forest_gate_kernel(ScanArgs a) {
+    if (a.status->overflow) return;
+    __shared__ int s_lst[kInline][kTile];
+    const int np = *a.d_np;
+    const int ntiles = (np + kTile - 1) / kTile;
+    const int lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int plane_cur = a.scan % a.W;
+    const GridDesc g = *a.grid;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int i = tile * kTile + tid;
+        int t = -1, n = 0;
+        bool heavy = false;
+        if (i < np) {
+            t = locate_tree(a, i, a.tile_tree[tile], a.tile_tree[tile + 1]);
+            const int pos = a.cur.par_lo[t] + (i - a.cur.par_off[t]);
+            LeafKF kf;
+            int ent;
+            load_leaf(a, t, pos, kf, ent);
+            int cx0, cx1, cy0, cy1;
+            if (gate_box(g, kf, cx0, cx1, cy0, cy1)) {
+                heavy = cy1 - cy0 + 1 > a.heavy_rows;
+                if (!heavy) {
+                    int ncand = 0;
+                    for (int cy = cy0; cy <= cy1; ++cy)
+                        ncand += a.cell_start[cy * g.nx + cx1 + 1] - a.cell_start[cy * g.nx + cx0];
+                    heavy = ncand > a.heavy_cand;
+                }
+                if (!heavy) {
+                    for_each_gated_box(g, a.cell_start, a.gz, a.gidx, kf, a.model.eta2, cx0, cx1, cy0, cy1,
+                                       [&](int m, double, double, double) {
+                                           if (n < kInline) s_lst[n][tid] = m;
+                                           ++n;
+                                       });
+                    heavy = n > kInline;
+                }
+            }
+            if (!heavy) a.count[i] = n + 1;
+        }
+        // worklist of heavy leaves, one atomic per warp
+        const unsigned hm = __ballot_sync(0xffffffffu, heavy);
+        if (hm) {
+            int base = 0;
+            if (lane == __ffs(hm) - 1) base = atomicAdd(a.heavy_n, __popc(hm));
+            base = __shfl_sync(0xffffffffu, base, __ffs(hm) - 1);
+            if (heavy) a.heavy_list[base + __popc(hm & ((1u << lane) - 1))] = make_int2(i, t);
+        }
+        if (heavy) n = 0;
+        // sort (network size chosen per warp), store, link
+        const int t_up = __shfl_up_sync(0xffffffffu, t, 1);
+        int4 *dst = (int4 *)(a.glist + (size_t)kInline * i);
+        if (__any_sync(0xffffffffu, n > 8)) {
+            int r[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) r[q] = q < n ? s_lst[q][tid] : 0x7fffffff;
+            sort_net<16>(r);
+#pragma unroll
+            for (int q = 0; q < 16; q += 4)
+                if (q < n) dst[q >> 2] = make_int4(r[q], r[q + 1], r[q + 2], r[q + 3]);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int m_up = __shfl_up_sync(0xffffffffu, r[q], 1);
+                if (q < n && !(lane > 0 && m_up == r[q] && t_up == t)) link_new_row(a, plane_cur, t, r[q]);
+            }
+        } else {
+            int r[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) r[q] = q < n ? s_lst[q][tid] : 0x7fffffff;
+            sort_net<8>(r);
+#pragma unroll
+            for (int q = 0; q < 8; q += 4)
+                if (q < n) dst[q >> 2] = make_int4(r[q], r[q + 1], r[q + 2], r[q + 3]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int m_up = __shfl_up_sync(0xffffffffu, r[q], 1);
+                if (q < n && !(lane > 0 && m_up == r[q] && t_up == t)) link_new_row(a, plane_cur, t, r[q]);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void link_new_row(const ScanArgs &a, int plane_cur, int t, int m) {
+    unsigned *word = a.tm_bits + (size_t)t * a.tm_words + (m >> 5);
+    const unsigned bit = 1u << (m & 31);
+    if (*word & bit) return;
+    if (atomicOr(word, bit) & bit) return;
+    a.used[m] = 1;
+    uf_touch_row(a.uf, a.row_owner, a.row_multi, plane_cur * a.max_meas + m, t);
+}
+
+// pass 1b -- heavy leaves, one WARP per leaf: lanes stride over the candidate measurements of every grid
+// row under the gate box, the gated indices are ranked (ascending) and written to a run of the pool;
+// glist[leaf][0] = start of the run.
+constexpr int kHeavyStage = 512;  // gated indices staged in shared memory per warp
+__global__ void __launch_bounds__(kTile) forest_gate_heavy_kernel(ScanArgs a, int *pool, long long pool_cap) {
+    if (a.status->overflow) return;
+    __shared__ int s_stage[kTile / 32][kHeavyStage];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nh = *a.heavy_n;
+    const int plane_cur = a.scan % a.W;
+    const GridDesc g = *a.grid;
+    const unsigned lt = (1u << lane) - 1;
+    for (int h = blockIdx.x * (kTile / 32) + wib; h < nh; h += gridDim.x * (kTile / 32)) {
+        const int2 it = a.heavy_list[h];
+        const int i = it.x, t = it.y;
+        const int pos = a.cur.par_lo[t] + (i - a.cur.par_off[t]);
+        LeafKF kf;
+        int ent;
+        load_leaf(a, t, pos, kf, ent);
+        int cx0, cx1, cy0, cy1;
+        gate_box(g, kf, cx0, cx1, cy0, cy1);   // true: the leaf was sent here because its box is large
+        // pass A: count
+        int n = 0;
+        for (int cy = cy0; cy <= cy1; ++cy) {
+            const int beg = a.cell_start[cy * g.nx + cx0], end = a.cell_start[cy * g.nx + cx1 + 1];
+            for (int p0 = beg; p0 < end; p0 += 32) {
+                const int p = p0 + lane;
+                bool ok = false;
+                if (p < end) {
+                    const double2 z = a.gz[p];
+                    ok = nis_f64(kf.si, z.x - kf.zhat[0], z.y - kf.zhat[1]) <= a.model.eta2;
+                }
+                n += __popc(__ballot_sync(0xffffffffu, ok));
+            }
+        }
+        const bool staged = n <= kHeavyStage, inl = n <= kInline;
+        long long off = 0;
+        if (!inl) {
+            if (lane == 0) off = atomicAdd((unsigned long long *)a.pool_ctr, (unsigned long long)(staged ? n : 2 * n));
+            off = __shfl_sync(0xffffffffu, off, 0);
+            if (off + (staged ? n : 2 * n) > pool_cap) {   // more children than the level can hold anyway
+                if (lane == 0) a.status->overflow = 2;
+                continue;
+            }
+        }
+        // pass B: collect (grid order), then rank
+        int *buf = staged ? s_stage[wib] : pool + off + n;
+        int *out = inl ? a.glist + (size_t)kInline * i : pool + off;   // few gated after all: inline list
+        int k = 0;
+        for (int cy = cy0; cy <= cy1; ++cy) {
+            const int beg = a.cell_start[cy * g.nx + cx0], end = a.cell_start[cy * g.nx + cx1 + 1];
+            for (int p0 = beg; p0 < end; p0 += 32) {
+                const int p = p0 + lane;
+                bool ok = false;
+                int m = 0;
+                if (p < end) {
+                    const double2 z = a.gz[p];
+                    m = a.gidx[p];
+                    ok = nis_f64(kf.si, z.x - kf.zhat[0], z.y - kf.zhat[1]) <= a.model.eta2;
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, ok);
+                if (ok) buf[k + __popc(mask & lt)] = m;
+                k += __popc(mask);
+            }
+        }
+        __syncwarp();
+        for (int e = lane; e < n; e += 32) {
+            const int m = buf[e];
+            int rank = 0;
+            for (int q = 0; q < n; ++q) rank += buf[q] < m;
+            out[rank] = m;
+            link_new_row(a, plane_cur, t, m);
+        }
+        if (lane == 0) {
+            a.count[i] = n + 1;
+            if (!inl) a.glist[(size_t)kInline * i] = (int)off;
+        }
+        __syncwarp();
+    }
+}
+
+// pass 1c: children counts -> tile-local exclusive offsets + per-tile sums
+__global__ void __launch_bounds__(kTile) forest_count_scan_kernel(ScanArgs a) {
     if (a.status->overflow) return;
     const int np = *a.d_np;
     const int ntiles = (np + kTile - 1) / kTile;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int i = tile * kTile + threadIdx.x;
-        // tree range of the tile (uniform searches: broadcast loads)
-        const int t_lo = locate_tree(a, tile * kTile, 0, a.T - 1);
-        const int t_hi = locate_tree(a, min(np, tile * kTile + kTile) - 1, t_lo, a.T - 1);
-        int cnt = 0;
-        if (i < np) {
-            const int t = locate_tree(a, i, t_lo, t_hi);
-            const int pos = a.cur.par_lo[t] + (i - a.cur.par_off[t]);
-            LeafKF kf;
-            int ent;
-            load_leaf(a, t, pos, kf, ent);
-            int lst[kInline];
-#pragma unroll
-            for (int q = 0; q < kInline; ++q) lst[q] = 0x7fffffff;
-            cnt = 1;
-            for_each_gated(*a.grid, a.cell_start, a.gz, a.gidx, kf, a.model.eta2,
-                           [&](int m, double, double, double) {
-                               ++cnt;
-                               int v = m;
-#pragma unroll
-                               for (int q = 0; q < kInline; ++q) {
-                                   const int lo = min(lst[q], v);
-                                   v = max(lst[q], v);
-                                   lst[q] = lo;
-                               }
-                           });
-            int4 *dst = (int4 *)(a.glist + (size_t)kInline * i);
-            dst[0] = make_int4(lst[0], lst[1], lst[2], lst[3]);
-            dst[1] = make_int4(lst[4], lst[5], lst[6], lst[7]);
-        }
+        const int cnt = (i < np) ? a.count[i] : 0;
         int total;
         const int excl = block_scan_excl(cnt, &total);
         if (i < np) a.count[i] = excl;
-        if (threadIdx.x == 0) {
-            a.tile_sum[tile] = total;
-            a.tile_tree[tile] = t_lo;
-        }
+        if (threadIdx.x == 0) a.tile_sum[tile] = total;
         __syncthreads();
     }
 }
@@ -369,11 +550,10 @@ __global__ void __launch_bounds__(1024, 1) forest_scan_tiles_kernel(ScanArgs a) 
 // pass 2: write the new level.  Child order per leaf = [miss, gated by ascending measurement index]
 // (Target.spawnNewNodes, pyTarget.py:239-254).  Every WARP owns 32 consecutive live leaves and never
 // synchronises with the rest of its CTA (child offsets come from pass 1):
-//   phase A (lane = leaf): state prediction, pattern-table entry, inherited path planes, cluster links
-//            (and, for the rare leaf with more than kInline gated measurements, the gate again, unsorted
-//            into HBM scratch);
-//   phase B (lane = CHILD, consecutive lanes = consecutive children): measurement from the parent's inline
-//            list, filter, score, and every field stored coalesced.
+//   phase A (lane = leaf): state prediction, pattern-table entry, inherited path planes and their
+//            cluster links;
+//   phase B (lane = CHILD, consecutive lanes = consecutive children): measurement from the parent's sorted
+//            list (inline, or its run in the pool), filter, score, and every field stored coalesced.
 constexpr int kEmitD = 8;    // doubles per leaf in smem: xbar[4] zhat[2] base_cnllr miss_cnllr
 __host__ __device__ inline size_t emit_warp_bytes(int W) {
     return (size_t)32 * kEmitD * 8 + (size_t)(3 + W) * 32 * 4 + 36 * 4;
@@ -381,7 +561,7 @@ __host__ __device__ inline size_t emit_warp_bytes(int W) {
 __host__ __device__ inline size_t emit_smem_bytes(int W) { return (kTile / 32) * emit_warp_bytes(W); }
 
 template <int WMAX>
-__global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, int *scratch) {
+__global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, const int *__restrict__ pool) {
     if (a.status->overflow) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -411,9 +591,7 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, int *scr
         if (lane == 0) s_off[32] = total;
         int t = -1, pos = 0, root_scan = 0x7fffffff;
         if (valid) {
-            const int t_lo = a.tile_tree[tile];
-            const int t_hi = (tile + 1 < ntiles) ? a.tile_tree[tile + 1] : a.T - 1;
-            t = locate_tree(a, i, t_lo, t_hi);
+            t = locate_tree(a, i, a.tile_tree[tile], a.tile_tree[tile + 1]);
             pos = a.cur.par_lo[t] + (i - a.cur.par_off[t]);
             root_scan = a.ts.root_scan[t];
         }
@@ -441,12 +619,6 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, int *scr
             s_tree[lane] = t;
             s_ent[lane] = ent;
             s_pat[lane] = (int)a.prev.pat[pos];
-            if (off_n - off_i - 1 > kInline) {  // rare: gate again, unsorted, into the leaf's scratch run
-                int k = 0;
-                int *dst = scratch + off_i + 1;
-                for_each_gated(*a.grid, a.cell_start, a.gz, a.gidx, kf, a.model.eta2,
-                               [&](int m, double, double, double) { dst[k++] = m; });
-            }
         }
         // cluster step (tracker.py:961-974): every measurement on the path links this tree to the other
         // trees using it; leaves are sorted by path, so a lane repeats its left neighbour's (row, tree)
@@ -478,25 +650,10 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, int *scr
             int g = first, row_new = -1, m = -1;
             if (live && k > 0) {
                 const int nsib = s_off[p + 1] - s_off[p] - 1;
-                if (nsib <= kInline) {
-                    m = a.glist[(size_t)kInline * ip + (k - 1)];
-                    g = first + k;
-                } else {
-                    const int *lst = scratch + first;
-                    m = lst[k];
-                    int rank = 0;
-                    for (int q = 1; q <= nsib; ++q) rank += lst[q] < m;
-                    g = first + 1 + rank;
-                }
+                const int *lst = a.glist + (size_t)kInline * ip;
+                m = (nsib <= kInline) ? lst[k - 1] : pool[lst[0] + (k - 1)];   // heavy leaves: run in the pool
+                g = first + k;
                 row_new = plane_cur * a.max_meas + m;
-            }
-            // one lane per distinct (tree, new row) of this batch marks the measurement used and links
-            // the tree to the row's other users
-            const long long key = m >= 0 ? (((long long)t_p << 32) | (unsigned)row_new) : (long long)(-1 - lane);
-            const unsigned grp = __match_any_sync(0xffffffffu, key);
-            if (m >= 0 && (int)(__ffs(grp) - 1) == lane) {
-                if (a.used[m] == 0) a.used[m] = 1;
-                uf_touch_row(a.uf, a.row_owner, a.row_multi, row_new, t_p);
             }
             if (!live) continue;
             double xo0 = s_d[0 * 32 + p], xo1 = s_d[1 * 32 + p], xo2 = s_d[2 * 32 + p], xo3 = s_d[3 * 32 + p];
@@ -768,12 +925,15 @@ static int forest_layout(mht_forest *f, bool commit) {
     f->pt_gate = carve<PatGate>(p, (int64_t)T * f->PT);
     f->pt_P = carve<float>(p, 16 * (int64_t)T * f->PT);
     f->tile_tree = carve<int>(p, f->cap_par / kTile + 4);
-    f->glist = carve<int>(p, 8 * (f->cap_par + 1));
+    f->glist = carve<int>(p, 16 * (f->cap_par + 1));
+    f->heavy_list = carve<int2>(p, f->cap_par + 1);
+    f->tm_words = (f->cfg.max_meas + 31) / 32;
+    f->tm_bits = carve<unsigned>(p, (int64_t)T * f->tm_words);
     f->out_d_base = p;
     carve_out(p, T, &f->out_d);
     f->out_bytes = p - f->out_d_base;
     f->status_d = carve<ScanStatus>(p, 1);
-    f->d_np = carve<int>(p, 2);
+    f->d_np = carve<int>(p, 8);   // d_np, d_nc, heavy_n, pad, pool_ctr (8 bytes)
     f->d_nc = f->d_np + 1;
     f->count = carve<int>(p, f->cap_par + 1);
     f->tile_sum = carve<int>(p, f->cap_par / kTile + 4);
@@ -861,6 +1021,15 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     a.tile_sum = f->tile_sum;
     a.tile_tree = f->tile_tree;
     a.glist = f->glist;
+    a.heavy_list = f->heavy_list;
+    a.tm_bits = f->tm_bits;
+    a.tm_words = f->tm_words;
+    static const int heavy_rows = getenv("MHT_HEAVY_ROWS") ? atoi(getenv("MHT_HEAVY_ROWS")) : 6;
+    static const int heavy_cand = getenv("MHT_HEAVY_CAND") ? atoi(getenv("MHT_HEAVY_CAND")) : 40;
+    a.heavy_rows = heavy_rows;
+    a.heavy_cand = heavy_cand;
+    a.heavy_n = f->d_np + 2;
+    a.pool_ctr = (long long *)(f->d_np + 4);
     a.pt_gate = f->pt_gate;
     a.pt_P = f->pt_P;
     a.PT = f->PT;
@@ -897,10 +1066,13 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     MHT_CUDA(cudaMemsetAsync(f->aw.u + (size_t)(k % f->W) * f->cfg.max_meas, 0, sizeof(double) * f->cfg.max_meas, s));
     if (int rc = assoc_begin(c, f->aw, grid_dim, s, k > 1)) return rc;
     MHT_CUDA(cudaMemsetAsync(f->used_d, 0, (size_t)(M ? M : 1), s));
+    MHT_CUDA(cudaMemsetAsync(f->tm_bits, 0, sizeof(unsigned) * (size_t)f->T * f->tm_words, s));
     live_scan_kernel<<<1, 1024, 0, s>>>(a);
     pat_table_kernel<<<f->T, 128, 0, s>>>(a);
     if (int rc = launch_grid_build(d_z, (int)M, grid, cell_start, cell_fill, gz, gidx, s)) return rc;
-    forest_count_kernel<<<grid_dim, kTile, 0, s>>>(a);
+    forest_gate_kernel<<<grid_dim, kTile, 0, s>>>(a);
+    forest_gate_heavy_kernel<<<grid_dim, kTile, 0, s>>>(a, (int *)f->aw.rc, 2 * (long long)f->cap_nodes);
+    forest_count_scan_kernel<<<grid_dim, kTile, 0, s>>>(a);
     forest_scan_tiles_kernel<<<1, 1024, 0, s>>>(a);
     if (f->W <= 8) forest_emit_kernel<8><<<grid_dim, kTile, emit_smem_bytes(f->W), s>>>(a, (int *)f->aw.rc);
     else forest_emit_kernel<MHT_MAX_WINDOW><<<grid_dim, kTile, emit_smem_bytes(f->W), s>>>(a, (int *)f->aw.rc);
