@@ -170,6 +170,34 @@ int mht_forest_scan(mht_forest *f, int64_t M, const double *h_z, double scan_tim
  * 64-byte status word: the kernel-only leg bench.py times as `value`. */
 int mht_forest_scan_device(mht_forest *f, int64_t M, const double *d_z, double scan_time, mht_scan_info *info);
 
+/* ------------------------------------------------------------------------------------------------
+ * Tree-sharded forests: N ranks each own a contiguous range of the trees of ONE
+ * surveillance region and receive the same scan.  The gate stage (Tracker._growTarget,
+ * tracker.py:207-209,309-351) is independent per tree; trees couple only through shared measurement
+ * rows of the 0/1 program (Tracker._createA1, tracker.py:1042-1113).  One scan is therefore
+ *   mht_forest_grow            (every rank, its own trees)
+ *   mht_forest_export_columns  (every rank writes its columns into caller-owned GLOBAL column arrays,
+ *                               at its column offset; the caller all-gathers the arrays, e.g. NCCL)
+ *   mht_assoc_solve            (global columns -> selected column per global tree)
+ *   mht_forest_select          (every rank, its slice of the selection: report, terminate, N-scan prune)
+ * Measurement row ids are plane * max_meas + index with plane = scan mod (N+1): identical on every rank
+ * that was created with the same configuration and has seen the same scans.
+ * ---------------------------------------------------------------------------------------------- */
+/* Gate stage only.  z = [M,2] f64, host (z_on_device = 0) or device.  info gets n_parents / n_children /
+ * n_pairs / ms_gate.  The scan stays open until mht_forest_select. */
+int mht_forest_grow(mht_forest *f, int64_t M, const double *z, int32_t z_on_device, double scan_time,
+                    mht_scan_info *info, uint8_t *h_meas_used);
+/* Columns of the open scan, in this forest's leaf order: d_cost[col_offset + j] = cNLLR_j - cNLLR_root
+ * (= N * c_j of tracker.py:1124-1136), d_tree[col_offset + j] = tree slot + tree_offset,
+ * d_rows[w * stride + col_offset + j] = measurement row of path plane w (< 0: none), w < N+1. */
+int mht_forest_export_columns(mht_forest *f, int32_t tree_offset, int64_t col_offset, int64_t stride,
+                              double *d_cost, int32_t *d_tree, int32_t *d_rows);
+/* Close the open scan with an externally computed selection: d_selected_col[t] = LOCAL column index
+ * (position in this forest's leaf order) for every tree slot t < n slots (ignored for dead slots).
+ * h_assoc_info = the 8 doubles of mht_assoc_solve (may be NULL); fills info like mht_forest_scan. */
+int mht_forest_select(mht_forest *f, const int32_t *d_selected_col, const double *h_assoc_info,
+                      mht_scan_info *info);
+
 /* Selected hypothesis per live tree after the last scan (Tracker.getTrackNodes, tracker.py:976):
  * h_slot[T] tree slot, h_x[T,4], h_P[T,16], h_cnllr[T], h_meas[T] (measurementNumber, 0 = miss),
  * h_status[T] (0 active, 1 out-of-range, 2 too-low-score; dead tracks are reported once, in the scan

@@ -70,6 +70,9 @@ _SIGNATURES = {
     "mht_forest_initiate": (C.c_int, [_vp, _vp, _vp, _dbl, C.POINTER(_i32)]),
     "mht_forest_scan": (C.c_int, [_vp, _i64, _vp, _dbl, C.POINTER(ScanInfo), _vp]),
     "mht_forest_scan_device": (C.c_int, [_vp, _i64, _vp, _dbl, C.POINTER(ScanInfo)]),
+    "mht_forest_grow": (C.c_int, [_vp, _i64, _vp, _i32, _dbl, C.POINTER(ScanInfo), _vp]),
+    "mht_forest_export_columns": (C.c_int, [_vp, _i32, _i64, _i64, _vp, _vp, _vp]),
+    "mht_forest_select": (C.c_int, [_vp, _vp, _vp, C.POINTER(ScanInfo)]),
     "mht_forest_tracks": (C.c_int, [_vp, _i32, C.POINTER(_i32), _vp, _vp, _vp, _vp, _vp, _vp]),
     "mht_forest_history": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i32), _vp, _vp, _vp, _vp]),
     "mht_forest_min_leaf_distance": (C.c_int, [_vp, _dbl, _dbl, C.POINTER(_dbl)]),

@@ -113,6 +113,9 @@ struct mht_forest {
     std::vector<std::vector<TrunkNode>> trunk;
     int64_t h_level_nodes;     // nodes in the current level (for initiate)
     std::vector<int> last_tracks;  // tree slots reported by the last scan
+    bool open_scan = false;        // mht_forest_grow done, mht_forest_select pending
+    int64_t open_M = 0, open_children = 0;
+    int64_t h_level_nodes_open() const { return open_children; }
 };
 
 namespace mht {
@@ -974,16 +977,23 @@ static void fill_update_args(mht_forest *f, UpdateArgs *u) {
     u->py = f->cfg.position[1];
 }
 
+// phase: 0 = whole scan; 1 = grow only (gate stage; the caller exchanges columns and calls the finish
+// phase through mht_forest_select); 2 = finish only (selection already in aw.sel; ext = the 8 doubles
+// mht_assoc_solve reports, or null).
 static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_scan_info *info,
-                            unsigned char *h_used) {
+                            unsigned char *h_used, int phase = 0, const double *ext = nullptr) {
     if (M < 0 || M > f->cfg.max_meas) {
         set_error("mht_forest_scan: %lld measurements exceed max_meas=%d", (long long)M, f->cfg.max_meas);
         return MHT_E_CAPACITY;
     }
     cudaStream_t s = f->stream;
-    const int k = f->scan + 1;
+    const int k = phase == 2 ? f->scan : f->scan + 1;
     if (f->T == 0) {  // no trees yet: the scan only advances the clock (tracker.py:207 loops over nothing)
-        f->scan = k;
+        if (phase != 2) f->scan = k;
+        if (phase == 1) {
+            f->open_scan = true;
+            f->open_children = 0;
+        }
         f->h_level_nodes = 0;
         f->last_tracks.clear();
         if (info) memset(info, 0, sizeof(*info));
@@ -992,10 +1002,10 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     }
     ScanArgs a;
     a.model = f->cfg.model;
-    a.prev = f->lv[f->scan % f->nslots];
+    a.prev = f->lv[(k - 1) % f->nslots];
     a.cur = f->lv[k % f->nslots];
     a.ts = f->ts;
-    a.rows_prev = f->rows[f->scan & 1];
+    a.rows_prev = f->rows[(k - 1) & 1];
     a.rows_cur = f->rows[k & 1];
     a.stride = f->cap_nodes;
     a.W = f->W;
@@ -1045,7 +1055,7 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     a.row_multi = f->aw.row_mark;
 
     const int grid_dim = kSMs * 8;
-    MHT_CUDA(cudaEventRecord(f->ev[0], s));
+    if (phase != 2) MHT_CUDA(cudaEventRecord(f->ev[0], s));
     ColView c;
     c.n_ptr = f->d_nc;
     c.idx = nullptr;
@@ -1061,31 +1071,64 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     c.n_rows = f->W * f->cfg.max_meas;
     assoc_carve(f->assoc_ws, f->cap_nodes, f->cfg.max_trees, (int64_t)f->W * f->cfg.max_meas, f->aw.cap_cand,
                 &f->aw);
-    // warm start: measurement rows keep their ids for W scans, so last scan's multipliers are a good
-    // starting point; the plane being recycled for this scan starts from zero
-    MHT_CUDA(cudaMemsetAsync(f->aw.u + (size_t)(k % f->W) * f->cfg.max_meas, 0, sizeof(double) * f->cfg.max_meas, s));
-    if (int rc = assoc_begin(c, f->aw, grid_dim, s, k > 1)) return rc;
-    MHT_CUDA(cudaMemsetAsync(f->used_d, 0, (size_t)(M ? M : 1), s));
-    MHT_CUDA(cudaMemsetAsync(f->tm_bits, 0, sizeof(unsigned) * (size_t)f->T * f->tm_words, s));
-    live_scan_kernel<<<1, 1024, 0, s>>>(a);
-    pat_table_kernel<<<f->T, 128, 0, s>>>(a);
-    if (int rc = launch_grid_build(d_z, (int)M, grid, cell_start, cell_fill, gz, gidx, s)) return rc;
-    forest_gate_kernel<<<grid_dim, kTile, 0, s>>>(a);
-    forest_gate_heavy_kernel<<<grid_dim, kTile, 0, s>>>(a, (int *)f->aw.rc, 2 * (long long)f->cap_nodes);
-    forest_count_scan_kernel<<<grid_dim, kTile, 0, s>>>(a);
-    forest_scan_tiles_kernel<<<1, 1024, 0, s>>>(a);
-    if (f->W <= 8) forest_emit_kernel<8><<<grid_dim, kTile, emit_smem_bytes(f->W), s>>>(a, (int *)f->aw.rc);
-    else forest_emit_kernel<MHT_MAX_WINDOW><<<grid_dim, kTile, emit_smem_bytes(f->W), s>>>(a, (int *)f->aw.rc);
-    tree_off_kernel<<<(f->T + 256) / 256, 256, 0, s>>>(a);
+    if (phase != 2) {
+        // warm start: measurement rows keep their ids for W scans, so last scan's multipliers are a good
+        // starting point; the plane being recycled for this scan starts from zero
+        MHT_CUDA(cudaMemsetAsync(f->aw.u + (size_t)(k % f->W) * f->cfg.max_meas, 0, sizeof(double) * f->cfg.max_meas, s));
+        if (int rc = assoc_begin(c, f->aw, grid_dim, s, k > 1)) return rc;
+        MHT_CUDA(cudaMemsetAsync(f->used_d, 0, (size_t)(M ? M : 1), s));
+        MHT_CUDA(cudaMemsetAsync(f->tm_bits, 0, sizeof(unsigned) * (size_t)f->T * f->tm_words, s));
+        live_scan_kernel<<<1, 1024, 0, s>>>(a);
+        pat_table_kernel<<<f->T, 128, 0, s>>>(a);
+        if (int rc = launch_grid_build(d_z, (int)M, grid, cell_start, cell_fill, gz, gidx, s)) return rc;
+        forest_gate_kernel<<<grid_dim, kTile, 0, s>>>(a);
+        forest_gate_heavy_kernel<<<grid_dim, kTile, 0, s>>>(a, (int *)f->aw.rc, 2 * (long long)f->cap_nodes);
+        forest_count_scan_kernel<<<grid_dim, kTile, 0, s>>>(a);
+        forest_scan_tiles_kernel<<<1, 1024, 0, s>>>(a);
+        if (f->W <= 8) forest_emit_kernel<8><<<grid_dim, kTile, emit_smem_bytes(f->W), s>>>(a, (int *)f->aw.rc);
+        else forest_emit_kernel<MHT_MAX_WINDOW><<<grid_dim, kTile, emit_smem_bytes(f->W), s>>>(a, (int *)f->aw.rc);
+        tree_off_kernel<<<(f->T + 256) / 256, 256, 0, s>>>(a);
+    }
     MHT_CUDA(cudaGetLastError());
-    MHT_CUDA(cudaEventRecord(f->ev[1], s));
+    if (phase != 2) MHT_CUDA(cudaEventRecord(f->ev[1], s));
 
     f->scan = k;
     static const long long sift_min = getenv("MHT_SIFT_MIN") ? atoll(getenv("MHT_SIFT_MIN")) : 1000000;
     const bool sift = f->h_level_nodes > sift_min;  // last scan's hypothesis count is the size hint
-    if (int rc = assoc_solve(c, f->aw, f->cfg.max_dual_iters, 400000, kSMs * 8, s, f->ev[5], f->scan > 1, sift, true))
-        return rc;
+    if (phase == 1) {  // grow only: report the level's size, keep the scan open
+        MHT_CUDA(cudaMemcpyAsync(f->status_h, f->status_d, sizeof(ScanStatus), cudaMemcpyDeviceToHost, s));
+        if (h_used) MHT_CUDA(cudaMemcpyAsync(f->used_h, f->used_d, (size_t)M, cudaMemcpyDeviceToHost, s));
+        MHT_CUDA(cudaStreamSynchronize(s));
+        if (h_used && M) memcpy(h_used, f->used_h, (size_t)M);
+        const ScanStatus &g = *f->status_h;
+        if (g.overflow) {
+            set_error("mht_forest_grow: capacity exceeded (%s: need %d, have %lld); the forest is unchanged "
+                      "for this scan -- recreate it with larger max_nodes/max_parents",
+                      g.overflow == 1 ? "live leaves" : "hypotheses", g.overflow == 1 ? g.n_parents : g.n_children,
+                      (long long)(g.overflow == 1 ? f->cap_par : f->cap_nodes));
+            f->scan = k - 1;
+            return MHT_E_CAPACITY;
+        }
+        if (info) {
+            memset(info, 0, sizeof(*info));
+            info->n_parents = g.n_parents;
+            info->n_children = g.n_children;
+            info->n_pairs = (int64_t)g.n_children - g.n_parents;
+            cudaEventElapsedTime(&info->ms_gate, f->ev[0], f->ev[1]);
+        }
+        f->open_scan = true;
+        f->open_children = g.n_children;
+        return MHT_OK;
+    }
+    if (phase == 0) {
+        if (int rc = assoc_solve(c, f->aw, f->cfg.max_dual_iters, 400000, kSMs * 8, s, f->ev[5], f->scan > 1, sift,
+                                 true))
+            return rc;
+    } else {
+        MHT_CUDA(cudaEventRecord(f->ev[5], s));
+    }
     MHT_CUDA(cudaEventRecord(f->ev[2], s));
+    f->open_scan = false;
 
     UpdateArgs u;
     fill_update_args(f, &u);
@@ -1155,8 +1198,32 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
         cudaEventElapsedTime(&info->ms_assoc, f->ev[5], f->ev[2]);
         cudaEventElapsedTime(&info->ms_prune, f->ev[2], f->ev[4]);
         cudaEventElapsedTime(&info->ms_total, f->ev[0], f->ev[4]);
+        if (phase == 2) {  // the association was solved outside the forest (sharded trees)
+            info->n_clusters = info->n_multi_clusters = info->n_active = 0;
+            info->dual_iters = ext ? (int)ext[5] : 0;
+            info->certified = ext ? (int)ext[6] : 0;
+            info->n_candidates = ext ? (int64_t)ext[2] : 0;
+            info->n_components = ext ? (int)ext[3] : 0;
+            info->bb_nodes = ext ? (int64_t)ext[4] : 0;
+            info->max_component = ext ? (int)ext[7] : 0;
+            info->lower_bound = ext ? ext[0] : 0.0;
+            info->objective = ext ? ext[1] : 0.0;
+        }
     }
     return MHT_OK;
+}
+
+// this forest's columns (leaf hypotheses of the open scan) -> caller-owned global column arrays
+__global__ void export_columns_kernel(Level cur, const int *rows_cur, long long stride_in, int W, const int *d_nc,
+                                      const double *root_cnllr, int tree_offset, long long col_offset,
+                                      long long stride_out, double *cost, int *tree, int *rows) {
+    const int n = *d_nc;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int t = cur.tree[j];
+        cost[col_offset + j] = cur.cnllr[j] - root_cnllr[t];
+        tree[col_offset + j] = t + tree_offset;
+        for (int w = 0; w < W; ++w) rows[w * stride_out + col_offset + j] = rows_cur[w * stride_in + j];
+    }
 }
 
 }  // namespace mht
@@ -1310,6 +1377,56 @@ extern "C" int mht_forest_scan(mht_forest *f, int64_t M, const double *h_z, doub
     if (M) memcpy(f->z_h, h_z, 16 * (size_t)M);  // stage through pinned memory
     MHT_CUDA(cudaMemcpyAsync(f->z_d, f->z_h, 16 * (size_t)M, cudaMemcpyHostToDevice, f->stream));
     return forest_scan_impl(f, M, f->z_d, info, h_meas_used ? h_meas_used : nullptr);
+}
+
+extern "C" int mht_forest_grow(mht_forest *f, int64_t M, const double *z, int32_t z_on_device, double scan_time,
+                               mht_scan_info *info, uint8_t *h_meas_used) {
+    (void)scan_time;
+    if (!f || (M > 0 && !z) || f->open_scan) {
+        set_error("mht_forest_grow: invalid argument or a grown scan is still waiting for mht_forest_select");
+        return MHT_E_INVALID;
+    }
+    if (M < 0 || M > f->cfg.max_meas) {
+        set_error("mht_forest_grow: %lld measurements exceed max_meas=%d", (long long)M, f->cfg.max_meas);
+        return MHT_E_CAPACITY;
+    }
+    const double *d_z = z;
+    if (!z_on_device) {
+        if (M) memcpy(f->z_h, z, 16 * (size_t)M);
+        MHT_CUDA(cudaMemcpyAsync(f->z_d, f->z_h, 16 * (size_t)M, cudaMemcpyHostToDevice, f->stream));
+        d_z = f->z_d;
+    }
+    f->open_M = M;
+    return forest_scan_impl(f, M, d_z, info, h_meas_used, 1);
+}
+
+extern "C" int mht_forest_export_columns(mht_forest *f, int32_t tree_offset, int64_t col_offset, int64_t stride,
+                                         double *d_cost, int32_t *d_tree, int32_t *d_rows) {
+    if (!f || !d_cost || !d_tree || !d_rows || col_offset < 0 || stride < col_offset + f->h_level_nodes_open()) {
+        set_error("mht_forest_export_columns: invalid argument");
+        return MHT_E_INVALID;
+    }
+    if (f->T == 0) return MHT_OK;
+    export_columns_kernel<<<kSMs * 8, 256, 0, f->stream>>>(f->lv[f->scan % f->nslots], f->rows[f->scan & 1], f->cap_nodes,
+                                                         f->W, f->d_nc, f->ts.root_cnllr, tree_offset, col_offset, stride,
+                                                         d_cost, d_tree, d_rows);
+    MHT_CUDA(cudaGetLastError());
+    MHT_CUDA(cudaStreamSynchronize(f->stream));
+    return MHT_OK;
+}
+
+extern "C" int mht_forest_select(mht_forest *f, const int32_t *d_selected_col, const double *h_assoc_info,
+                                 mht_scan_info *info) {
+    if (!f || !f->open_scan || (f->T > 0 && !d_selected_col)) {
+        set_error("mht_forest_select: no grown scan is open (call mht_forest_grow first)");
+        return MHT_E_INVALID;
+    }
+    if (f->T > 0)
+        MHT_CUDA(cudaMemcpyAsync(f->aw.sel, d_selected_col, sizeof(int) * (size_t)f->T, cudaMemcpyDeviceToDevice,
+                                 f->stream));
+    const int rc = forest_scan_impl(f, f->open_M, f->z_d, info, nullptr, 2, h_assoc_info);
+    f->open_scan = false;
+    return rc;
 }
 
 extern "C" int mht_forest_scan_device(mht_forest *f, int64_t M, const double *d_z, double scan_time,

@@ -1,0 +1,171 @@
+"""Tree-sharded `Tracker`: N ranks of one `torch.distributed` group each own a contiguous
+slice of the track trees of ONE surveillance region and are fed the SAME scans.
+
+Per scan (reference pymht/tracker.py:194-259):
+  1. grow     every rank gates its own trees              (tracker.py:207-209, independent per tree)
+  2. exchange all ranks learn every rank's column count; each rank writes its columns
+              {cost, tree, <= N+1 measurement rows} into global column arrays at its offset and the
+              slices are broadcast (an all-gather with ragged sizes; NCCL over NVLink on GPUs)
+  3. solve    the global 0/1 program (tracker.py:228-236,979-1217) on the gathered columns -- trees couple
+              only through shared measurement rows (tracker.py:1042-1113); rank 0's selection is broadcast
+              so every shard applies the same global hypothesis
+  4. select   every rank closes the scan for its trees: report, terminate, N-scan prune
+
+Because rank r holds the trees [lo_r, hi_r) and the slices are concatenated in rank order, the global column
+order equals the single-forest order, so the sharded run reproduces the one-GPU tracks exactly.
+
+torch is used for what it is here for: device buffers and the process group.  The pure functions below
+(`shard_bounds`, `exchange_counts`, `gather_slices`, `local_selection`) run on any backend (gloo in the CPU tests).
+"""
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _lib
+from .tracker import Tracker
+from .pyTarget import Target, preinitializedTag
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous slice [lo, hi) of n items owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def exchange_counts(dist, torch, device, n_cols, n_trees, group=None):
+    """All ranks learn (columns, tree slots) of every rank.  Returns two int lists and the exclusive offsets."""
+    mine = torch.tensor([int(n_cols), int(n_trees)], dtype=torch.int64, device=device)
+    world = dist.get_world_size(group)
+    out = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    cols = [int(o[0]) for o in out]
+    trees = [int(o[1]) for o in out]
+    col_off = [0] + list(np.cumsum(cols)[:-1].astype(int)) if world else [0]
+    tree_off = [0] + list(np.cumsum(trees)[:-1].astype(int)) if world else [0]
+    return cols, trees, [int(v) for v in col_off], [int(v) for v in tree_off]
+
+
+def gather_slices(dist, tensors, counts, offsets, group=None):
+    """Ragged all-gather in place: every tensor's last dimension is the global column axis; rank r has filled
+    [offsets[r], offsets[r] + counts[r]) and receives the other ranks' slices by broadcast."""
+    for r, (cnt, off) in enumerate(zip(counts, offsets)):
+        if cnt == 0:
+            continue
+        for t in tensors:
+            if t.dim() == 1:
+                dist.broadcast(t[off:off + cnt], src=r, group=group)
+            else:
+                for w in range(t.shape[0]):      # a plane's slice is contiguous, the 2-D slice is not
+                    dist.broadcast(t[w, off:off + cnt], src=r, group=group)
+
+
+def local_selection(sel_global, tree_off, n_trees, col_off):
+    """Slice of the global selection for this rank's tree slots, as LOCAL column indices (-1 stays -1)."""
+    loc = sel_global[tree_off:tree_off + n_trees].clone()
+    loc[loc >= 0] -= col_off
+    return loc
+
+
+class ShardedTracker(Tracker):
+    def __init__(self, model, radarPeriod, lambda_phi, lambda_nu, group=None, **kwargs):
+        import torch
+        import torch.distributed as dist
+        self._torch, self._dist, self._group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._device = torch.device("cuda", torch.cuda.current_device())
+        super().__init__(model, radarPeriod, lambda_phi, lambda_nu, **kwargs)
+        self.exchangeLog = []          # per scan: dict(n_cols_global, bytes_gathered, ms_exchange, ms_solve)
+
+    def preInitialize(self, simList):
+        """This rank's contiguous slice of the ground-truth targets; track IDs stay global."""
+        targets = list(simList[0])
+        lo, hi = shard_bounds(len(targets), self.world, self.rank)
+        self.trackIdCounter = lo
+        for tgt in targets[lo:hi]:
+            self.initiateTarget(Target(tgt.time, None, np.asarray(tgt.cartesianState(), dtype=np.float64), self.P_0,
+                                       status=preinitializedTag))
+
+    def addMeasurementList(self, scanList, aisList=None, **kwargs):
+        torch, dist, lib = self._torch, self._dist, self._lib
+        if aisList is not None and len(aisList) > 0:
+            raise NotImplementedError("AIS fusion (tracker.py:417-552) is outside the accelerated path")
+        self.tic.clear()
+        self.toc.clear()
+        self.__scanHistory__.append(scanList)
+        t_total = time.time()
+        z = np.ascontiguousarray(scanList.measurements, dtype=np.float64).reshape(-1, 2)
+        nMeas = z.shape[0]
+        used = np.zeros(max(nMeas, 1), dtype=np.uint8)
+        ginfo = _lib.ScanInfo()
+        _lib.check(lib.mht_forest_grow(self._forest, nMeas, _lib.ptr(z), 0, float(scanList.time), C.byref(ginfo),
+                                       _lib.ptr(used)))
+        n_slots = self._n_slots()
+        t0 = time.time()
+        cols, trees, col_off, tree_off = exchange_counts(dist, torch, self._device, ginfo.n_children, n_slots,
+                                                         self._group)
+        n_total, t_total_slots = sum(cols), sum(trees)
+        W = self.N + 1
+        info = _lib.ScanInfo()
+        if n_total == 0 or t_total_slots == 0:
+            sel_local = torch.full((max(n_slots, 1),), -1, dtype=torch.int32, device=self._device)
+            _lib.check(lib.mht_forest_select(self._forest, sel_local.data_ptr(), None, C.byref(info)))
+            ext, ms_ex, ms_solve = None, 0.0, 0.0
+        else:
+            cost = torch.empty(n_total, dtype=torch.float64, device=self._device)
+            tree = torch.empty(n_total, dtype=torch.int32, device=self._device)
+            rows = torch.empty((W, n_total), dtype=torch.int32, device=self._device)
+            torch.cuda.current_stream().synchronize()
+            _lib.check(lib.mht_forest_export_columns(self._forest, tree_off[self.rank], col_off[self.rank], n_total,
+                                                     cost.data_ptr(), tree.data_ptr(), rows.data_ptr()))
+            gather_slices(dist, [cost, tree, rows], cols, col_off, self._group)
+            torch.cuda.current_stream().synchronize()
+            ms_ex = 1e3 * (time.time() - t0)
+            t1 = time.time()
+            n_rows = W * self.maxMeasurements
+            sel = torch.full((t_total_slots,), -1, dtype=torch.int32, device=self._device)
+            work = torch.empty(int(lib.mht_assoc_workspace(n_total, t_total_slots, n_rows, W)), dtype=torch.uint8,
+                               device=self._device)
+            ext = np.zeros(8)
+            _lib.check(lib.mht_assoc_solve(n_total, t_total_slots, n_rows, W, cost.data_ptr(), tree.data_ptr(),
+                                           rows.data_ptr(), sel.data_ptr(), _lib.ptr(ext), work.data_ptr(), None),
+                       allow=(_lib.MHT_E_NOTOPTIMAL,))
+            dist.broadcast(sel, src=0, group=self._group)     # one global hypothesis for every shard
+            torch.cuda.current_stream().synchronize()
+            ms_solve = 1e3 * (time.time() - t1)
+            sel_local = local_selection(sel, tree_off[self.rank], max(n_slots, 0), col_off[self.rank]).contiguous()
+            if n_slots == 0:
+                sel_local = torch.full((1,), -1, dtype=torch.int32, device=self._device)
+            _lib.check(lib.mht_forest_select(self._forest, sel_local.data_ptr(), _lib.ptr(ext), C.byref(info)))
+        d = info.as_dict()
+        d["ms_gate"] = ginfo.ms_gate
+        d["ms_assoc"] = ms_solve
+        self.scanInfo.append(d)
+        self.exchangeLog.append({"n_cols_global": n_total, "bytes_gathered": n_total * (12 + 4 * W),
+                                 "ms_exchange": ms_ex, "ms_solve": ms_solve})
+        self.toc["Process"] = ginfo.ms_gate * 1e-3
+        self.toc["Cluster"] = 0.0
+        self.toc["Optim"] = (ms_ex + ms_solve) * 1e-3
+        self.toc["ILP-Prune"] = self.toc["DynN"] = 0.0
+        t_term = time.time()
+        self._collect_tracks(scanList)
+        self.toc["Terminate"] = time.time() - t_term
+        self.toc["N-Prune"] = info.ms_prune * 1e-3
+        self.toc["Init"] = 0.0
+        self.toc["Total"] = time.time() - t_total
+        for k, v in self.runtimeLog.items():
+            if k in self.toc:
+                v.append(self.toc[k])
+
+    def _n_slots(self):
+        """Tree slots of the local forest (live and dead): slot s holds global tree tree_off + s."""
+        return len(self._slot_info)
+
+    def gatherTracks(self):
+        """Every rank's live tracks as (ID, measurementNumber, cumulativeNLLR, x_0), concatenated in rank order."""
+        mine = [(int(n.ID), int(n.measurementNumber), float(n.cumulativeNLLR), np.asarray(n.x_0).tolist())
+                for n in self.getTrackNodes()]
+        out = [None] * self.world
+        self._dist.all_gather_object(out, mine, group=self._group)
+        return [t for part in out for t in part]

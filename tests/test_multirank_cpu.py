@@ -41,3 +41,62 @@ def test_sector_sharding_and_exchange_world2():
     assert tdev0 == tdev1 == 2.0          # max over ranks
     assert te0 == te1 == 2.0
     assert tr0 == tr1 == [100, 101]       # every rank sees every sector's track count
+
+
+def _shard_worker(rank, world, port, out):
+    """The ragged column all-gather of pymht_b200.sharded on CPU tensors (gloo)."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pymht_b200 import sharded as sh
+    dev = torch.device("cpu")
+    n_items = 7                                           # 7 trees over 2 ranks -> 4 + 3
+    lo, hi = sh.shard_bounds(n_items, world, rank)
+    n_cols = [5, 3][rank]                                 # ragged column counts
+    cols, trees, col_off, tree_off = sh.exchange_counts(dist, torch, dev, n_cols, hi - lo)
+    n_total, W = sum(cols), 3
+    cost = torch.full((n_total,), -1.0, dtype=torch.float64)
+    tree = torch.full((n_total,), -1, dtype=torch.int32)
+    rows = torch.full((W, n_total), -9, dtype=torch.int32)
+    o = col_off[rank]
+    cost[o:o + n_cols] = torch.arange(n_cols, dtype=torch.float64) + 100 * rank
+    tree[o:o + n_cols] = tree_off[rank] + torch.arange(n_cols, dtype=torch.int32) % (hi - lo)
+    for w in range(W):
+        rows[w, o:o + n_cols] = 1000 * rank + 10 * w + torch.arange(n_cols, dtype=torch.int32)
+    sh.gather_slices(dist, [cost, tree, rows], cols, col_off)
+    sel_global = torch.tensor([0, 2, -1, 4, 5, -1, 7], dtype=torch.int32)       # column per global tree
+    loc = sh.local_selection(sel_global, tree_off[rank], hi - lo, col_off[rank])
+    out.put((rank, (lo, hi), cols, trees, col_off, tree_off, cost.tolist(), tree.tolist(), rows.tolist(), loc.tolist()))
+    dist.destroy_process_group()
+
+
+def test_tree_sharded_column_exchange_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    r0, r1 = res
+    assert r0[1] == (0, 4) and r1[1] == (4, 7)                  # contiguous tree slices
+    assert r0[2] == r1[2] == [5, 3] and r0[3] == r1[3] == [4, 3]
+    assert r0[4] == r1[4] == [0, 5] and r0[5] == r1[5] == [0, 4]
+    assert r0[6] == r1[6] == [0, 1, 2, 3, 4, 100, 101, 102]     # both ranks hold the same global columns
+    assert r0[7] == r1[7] == [0, 1, 2, 3, 0, 4, 5, 6]
+    assert r0[8] == r1[8]
+    assert r0[8][1] == [10, 11, 12, 13, 14, 1010, 1011, 1012]
+    assert r0[9] == [0, 2, -1, 4] and r1[9] == [0, -1, 2]       # global column -> local column
+
+
+def test_shard_bounds_cover_everything():
+    from pymht_b200 import sharded as sh
+    for n in (0, 1, 7, 1000):
+        for world in (1, 2, 3, 8):
+            b = [sh.shard_bounds(n, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
