@@ -189,6 +189,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3_1k_targets_5k_meas_N6", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="sectors", choices=["sectors", "trees"],
+                    help="N>1: 'sectors' = one independent region per rank (weak scaling, default); 'trees' = the "
+                         "trees of ONE region sharded over the ranks, column records all-gathered (strong scaling)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -222,9 +225,13 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     preroll = N + 2
     n_scans = preroll + args.warmup + args.steps
+    if args.shard == "trees" and world > 1:
+        return run_tree_sharded(args, name, config, dist, torch, rank, world, local_rank, preroll, n_scans)
     simList, scans = make_scenario(name, n_scans, seed_offset=rank)
 
     def barrier():
@@ -296,6 +303,55 @@ def main():
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_tree_sharded(args, name, config, dist, torch, rank, world, local_rank, preroll, n_scans):
+    """ONE region, its trees sharded over the ranks (pymht_b200/sharded.py): every rank gates its own trees, the
+    column records are all-gathered over NCCL, the global 0/1 program is solved on the gathered columns.  Timed
+    end to end through ShardedTracker.addMeasurementList (host scan in, tracks out), max over ranks."""
+    from pymht_b200.sharded import ShardedTracker
+    from pymht_b200.models import pv
+    nT, R, lam, N, Pd, seed, max_nodes, max_par = WORKLOADS[name]
+    simList, scans = make_scenario(name, n_scans, seed_offset=0)      # the same region on every rank
+    per = 1.0 / world + 0.15
+    trk = ShardedTracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=8192,
+                         maxNodes=int(max_nodes * per), maxParents=int(max_par * per),
+                         maxDualIterations=int(os.environ.get("MHT_DUAL_ITERS", "120")))
+    trk.mergeThreshold = 0.0
+    trk.preInitialize(simList)
+    times = []
+    for s in scans:
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        trk.addMeasurementList(s)
+        times.append(time.perf_counter() - t0)
+    timed = times[preroll + args.warmup:]
+    t = torch.tensor([sum(timed)], dtype=torch.float64, device=torch.device("cuda", local_rank))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    log = trk.exchangeLog[preroll + args.warmup:]
+    infos = trk.scanInfo[preroll + args.warmup:]
+    n_tracks = len(trk.gatherTracks())
+    if rank == 0:
+        K = len(timed)
+        v = K / float(t[0])
+        config = dict(config, parallelism="trees of one region sharded over %d GPUs; ragged all-gather of column "
+                      "records (NCCL) + replicated global solve" % world)
+        line = {"metric": "scans/sec @ 1k targets, 5k meas/scan", "value": v, "unit": "scans/s", "n_gpus": world,
+                "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64 state / f32 covariance", "data": "synthetic", "config": config,
+                "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": int(np.mean([16 * len(s.measurements) for s in scans])),
+                        "d2h_bytes_per_step": int(n_tracks * 152 + 128)},
+                "stage_ms": {"ms_gate_rank0": float(np.mean([d["ms_gate"] for d in infos])),
+                             "ms_exchange": float(np.mean([d["ms_exchange"] for d in log])),
+                             "ms_solve": float(np.mean([d["ms_solve"] for d in log]))},
+                "exchange": {"columns_global": float(np.mean([d["n_cols_global"] for d in log])),
+                             "bytes_gathered_per_scan": float(np.mean([d["bytes_gathered"] for d in log]))},
+                "scan_stats": {"tracks": n_tracks, "objective": float(np.mean([d["objective"] for d in infos])),
+                               "lower_bound": float(np.mean([d["lower_bound"] for d in infos]))}}
+        print(json.dumps(line))
+    trk.close()
+    dist.destroy_process_group()
 
 
 def exchange(dist, device, t_dev, t_e2e, n_tracks):
