@@ -587,11 +587,11 @@ __global__ void __launch_bounds__(1024, 1) greedy_finish_kernel(ColView c, Assoc
 // phases): `iters` subgradient iterations, a greedy primal pass every kGreedyEvery iterations whose
 // bidding rounds stop as soon as every tree is committed.  Replaces ~7 launches per iteration.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dual_loop_persistent_kernel(ColView c, AssocWork w, int iters) {
+__global__ void __launch_bounds__(256) dual_loop_persistent_kernel(ColView c, AssocWork w, int iters, int greedy_every) {
     cg::grid_group grid = cg::this_grid();
     for (int it = 0; it < iters; ++it) {
         if (((volatile int *)w.info)[0]) break;  // uniform: written before the last grid.sync
-        if (it % kGreedyEvery == 0) {
+        if (it % greedy_every == 0) {
             dual_rc_body<false>(c, w);
             grid.sync();
             for (int mode = 0; mode < (it ? 2 : 1); ++mode) {
@@ -1458,7 +1458,8 @@ static int persistent_grid() {
 static int dual_loop(const ColView &c, AssocWork &w, int iters, int grid_dim, cudaStream_t s) {
     ColView cc = c;
     AssocWork ww = w;
-    void *args[] = {&cc, &ww, &iters};
+    static int greedy_every = getenv("MHT_GREEDY_EVERY") ? atoi(getenv("MHT_GREEDY_EVERY")) : kGreedyEvery;
+    void *args[] = {&cc, &ww, &iters, &greedy_every};
     // grid.sync cost grows with the grid: the active list (~1e5 columns) gets one CTA per SM
     const int grid = grid_dim < persistent_grid() ? grid_dim : persistent_grid();
     MHT_CUDA(cudaLaunchCooperativeKernel((void *)dual_loop_persistent_kernel, dim3(grid), dim3(256), args,
@@ -1485,7 +1486,8 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
         a.n_ptr = w.act_n;
         static const int act_grid_env = getenv("MHT_ACT_GRID") ? atoi(getenv("MHT_ACT_GRID")) : 2 * kSMs;
         const int act_grid = act_grid_env;
-        for (int round = 0; round < kSiftRounds; ++round) {
+        static const int sift_rounds = getenv("MHT_SIFT_ROUNDS") ? atoi(getenv("MHT_SIFT_ROUNDS")) : kSiftRounds;
+        for (int round = 0; round < sift_rounds; ++round) {
             if (round) sift_rearm_kernel<<<1, 1024, 0, s>>>(c, w);
             dual_rc_kernel<true><<<grid_dim, 256, 0, s>>>(c, w);
             active_count_kernel<<<grid_dim, 256, 0, s>>>(c, w);

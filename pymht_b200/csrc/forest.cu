@@ -418,12 +418,21 @@ __global__ void __launch_bounds__(kTile, 4) forest_gate_kernel(ScanArgs a) {
 }
 
 __device__ __forceinline__ void link_new_row(const ScanArgs &a, int plane_cur, int t, int m) {
-    unsigned *word = a.tm_bits + (size_t)t * a.tm_words + (m >> 5);
-    const unsigned bit = 1u << (m & 31);
+    const int r = plane_cur * a.max_meas + m;
+    unsigned *word = a.tm_bits + (size_t)t * a.tm_words + (r >> 5);
+    const unsigned bit = 1u << (r & 31);
     if (*word & bit) return;
     if (atomicOr(word, bit) & bit) return;
     a.used[m] = 1;
-    uf_touch_row(a.uf, a.row_owner, a.row_multi, plane_cur * a.max_meas + m, t);
+    uf_touch_row(a.uf, a.row_owner, a.row_multi, r, t);
+}
+// same for a row inherited from the path (any plane)
+__device__ __forceinline__ void link_old_row(const ScanArgs &a, int t, int r) {
+    unsigned *word = a.tm_bits + (size_t)t * a.tm_words + (r >> 5);
+    const unsigned bit = 1u << (r & 31);
+    if (*word & bit) return;
+    if (atomicOr(word, bit) & bit) return;
+    uf_touch_row(a.uf, a.row_owner, a.row_multi, r, t);
 }
 
 // pass 1b -- heavy leaves, one WARP per leaf: lanes stride over the candidate measurements of every grid
@@ -559,7 +568,7 @@ __global__ void __launch_bounds__(1024, 1) forest_scan_tiles_kernel(ScanArgs a) 
 //            list (inline, or its run in the pool), filter, score, and every field stored coalesced.
 constexpr int kEmitD = 8;    // doubles per leaf in smem: xbar[4] zhat[2] base_cnllr miss_cnllr
 __host__ __device__ inline size_t emit_warp_bytes(int W) {
-    return (size_t)32 * kEmitD * 8 + (size_t)(3 + W) * 32 * 4 + 36 * 4;
+    return (size_t)32 * kEmitD * 8 + (size_t)(3 + W) * 32 * 4 + 36 * 4 + 32 * kInline * 4;
 }
 __host__ __device__ inline size_t emit_smem_bytes(int W) { return (kTile / 32) * emit_warp_bytes(W); }
 
@@ -574,9 +583,9 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, const in
     int *s_ent = s_tree + 32;                  // [32] pattern-table entry
     int *s_pat = s_ent + 32;                   // [32] hit/miss history of the leaf
     int *s_off = s_pat + 32;                   // [33] child offsets inside the warp (+3 pad)
-    int *s_path = s_off + 36;                  // [W][32]
+    int *s_lst = s_off + 36;                   // [32][kInline] the leaves' sorted gated lists
+    int *s_path = s_lst + 32 * kInline;        // [W][32]
     const int np = *a.d_np;
-    const int ntiles = (np + kTile - 1) / kTile;
     const int nwt = (np + 31) >> 5;
     const int W = a.W;
     const int plane_cur = a.scan % W;
@@ -608,6 +617,16 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, const in
             const bool take = w < W && back != 0 && a.scan - back > root_scan;
             rr[w] = take ? a.rows_prev[(long long)w * a.stride + pos] : -1;
         }
+        {   // the leaf's inline list -> shared memory (only the quarters that hold entries)
+            const int nl = off_n - off_i - 1;
+            if (valid && nl <= kInline) {
+                const int4 *src = (const int4 *)(a.glist + (size_t)kInline * i);
+                int4 *dst = (int4 *)(s_lst + kInline * lane);
+#pragma unroll
+                for (int q = 0; q < kInline / 4; ++q)
+                    if (4 * q < nl) dst[q] = src[q];
+            }
+        }
         if (valid) {
             LeafKF kf;
             int ent;
@@ -632,7 +651,7 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, const in
                 const int r = rr[w];
                 s_path[w * 32 + lane] = r;
                 const int r_up = __shfl_up_sync(0xffffffffu, r, 1), t_up = __shfl_up_sync(0xffffffffu, t, 1);
-                if (r >= 0 && !(lane > 0 && r_up == r && t_up == t)) uf_touch_row(a.uf, a.row_owner, a.row_multi, r, t);
+                if (r >= 0 && !(lane > 0 && r_up == r && t_up == t)) link_old_row(a, t, r);
             }
         }
         __syncwarp();
@@ -653,8 +672,8 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, const in
             int g = first, row_new = -1, m = -1;
             if (live && k > 0) {
                 const int nsib = s_off[p + 1] - s_off[p] - 1;
-                const int *lst = a.glist + (size_t)kInline * ip;
-                m = (nsib <= kInline) ? lst[k - 1] : pool[lst[0] + (k - 1)];   // heavy leaves: run in the pool
+                // heavy leaves: a run in the pool whose start is the first entry of the leaf's list
+                m = (nsib <= kInline) ? s_lst[kInline * p + (k - 1)] : pool[a.glist[(size_t)kInline * ip] + (k - 1)];
                 g = first + k;
                 row_new = plane_cur * a.max_meas + m;
             }
@@ -683,9 +702,12 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, const in
             a.cur.pidx[g] = ip;
             a.cur.tree[g] = t_p;
             a.cur.pat[g] = (unsigned short)(((s_pat[p] << 1) | (m >= 0)) & 0xffff);
+            int *col = a.rows_cur + g;
 #pragma unroll
-            for (int w = 0; w < WMAX; ++w)
-                if (w < W) a.rows_cur[(long long)w * a.stride + g] = (w == plane_cur) ? row_new : s_path[w * 32 + p];
+            for (int w = 0; w < WMAX; ++w) {
+                if (w < W) *col = (w == plane_cur) ? row_new : s_path[w * 32 + p];
+                col += a.stride;
+            }
         }
         __syncwarp();
     }
@@ -930,7 +952,7 @@ static int forest_layout(mht_forest *f, bool commit) {
     f->tile_tree = carve<int>(p, f->cap_par / kTile + 4);
     f->glist = carve<int>(p, 16 * (f->cap_par + 1));
     f->heavy_list = carve<int2>(p, f->cap_par + 1);
-    f->tm_words = (f->cfg.max_meas + 31) / 32;
+    f->tm_words = (int)(((int64_t)f->W * f->cfg.max_meas + 31) / 32);
     f->tm_bits = carve<unsigned>(p, (int64_t)T * f->tm_words);
     f->out_d_base = p;
     carve_out(p, T, &f->out_d);
