@@ -337,3 +337,60 @@ def test_determinism_same_inputs_same_outputs():
             out.append((hist, [n.cumulativeNLLR for n in nodes], info["objective"], info["lower_bound"]))
         runs.append(out)
     assert runs[0] == runs[1]
+
+
+def test_dense_gate_heavy_paths_vs_oracle():
+    """One target and a scan with 700 measurements inside its gate: exercises the warp-per-leaf gate kernel,
+    the pooled (more than 16 gated) lists and the unstaged (more than 512 gated) path; the children must come
+    out in ascending measurement order with the oracle's scores and states, also one scan later when every
+    one of those children is a parent."""
+    from pymht_b200.tracker import Tracker
+    from pymht_b200.models import pv
+    from pymht_b200.pyTarget import Target
+    from pymht_b200.utils.classDefinitions import MeasurementList
+    rng = np.random.RandomState(5)
+    x0 = np.array([50.0, -20.0, 2.0, 1.0])
+    trk = Tracker(pv, 2.5, 1e-3, 1e-9, N=3, P_d=0.9, maxTargets=8, maxNodes=1 << 20, maxParents=1 << 16,
+                  maxMeasurements=4096)
+    trk.mergeThreshold = 0.0
+    orc = mo.OracleTracker(2.5, 1e-3, 1e-9, eta2=5.99, N=3, P_d=0.9)
+    trk.initiateTarget(Target(0.0, None, x0, pv.P0))
+    orc.initiate(x0, 0.0)
+    centre = x0[:2] + 2.5 * x0[2:]
+    for k, (n_in, spread) in enumerate([(700, 6.0), (40, 9.0)]):
+        centre = centre + 2.5 * x0[2:] * k
+        z = np.concatenate([centre + rng.uniform(-spread, spread, (n_in, 2)), rng.uniform(-3000, 3000, (300, 2))])
+        z = z[rng.permutation(len(z))].astype(np.float32)
+        trk.addMeasurementList(MeasurementList(2.5 * (k + 1), z))
+        orc.n_scans += 1
+        orc._grow(z, 2.5 * (k + 1), orc.n_scans)
+        info = trk.scanInfo[-1]
+        want = orc.leaves[0]
+        assert info["n_children"] == len(want), (k, info["n_children"], len(want))
+        orc._select(orc._cluster())
+        orc._terminate()
+        orc._prune()
+        node, ref = trk.getTrackNodes()[0], orc.track_nodes()[0]
+        assert node.measurementNumber == ref.meas
+        np.testing.assert_allclose(node.x_0, ref.x, rtol=RTOL, atol=XATOL)
+        np.testing.assert_allclose(node.cumulativeNLLR, ref.cnllr, rtol=RTOL, atol=ATOL)
+        x, cn, meas = trk.getLeafNodes(0)
+        live = orc.leaves[0]
+        assert list(meas) == [l.meas for l in live], k
+        np.testing.assert_allclose(cn, [l.cnllr for l in live], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(x, np.array([l.x for l in live]), rtol=RTOL, atol=XATOL)
+    assert trk.scanInfo[0]["n_children"] > 513 and trk.scanInfo[1]["n_parents"] > 513
+    trk.close()
+
+
+def test_every_leaf_through_the_warp_per_leaf_gate():
+    """MHT_HEAVY_ROWS=0 / MHT_HEAVY_CAND=0 send EVERY leaf through forest_gate_heavy_kernel (the thresholds are
+    read once per process, hence the subprocess): the cfg2_small replay must still match the reference."""
+    import os, subprocess, sys
+    from conftest import ROOT
+    env = dict(os.environ, MHT_HEAVY_ROWS="0", MHT_HEAVY_CAND="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-x",
+                        "-m", "gpu", "-k", "replays and (cfg2_small or cfg5_small or cfg1)"], env=env, cwd=ROOT,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "3 passed" in r.stdout
