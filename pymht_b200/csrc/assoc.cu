@@ -422,8 +422,14 @@ static void dual_update(const ColView &c, AssocWork &w, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // primal greedy in parallel rounds
 // ------------------------------------------------------------------------------------------------
+// block 0 resets the per-tree state; the row arrays (n_rows entries) are cleared by the WHOLE grid
 __device__ __forceinline__ void greedy_init_body(ColView c, AssocWork w, const int *tstart) {
     if (w.info[0]) return;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < c.n_rows; r += gridDim.x * blockDim.x) {
+        w.row_taken[r] = 0;
+        w.row_bid[r] = kKeyInf;
+    }
+    if (blockIdx.x != 0) return;
     __shared__ int left;
     if (threadIdx.x == 0) left = 0;
     __syncthreads();
@@ -434,10 +440,6 @@ __device__ __forceinline__ void greedy_init_body(ColView c, AssocWork w, const i
         w.prop_col[t] = -1;
         w.sel_new[t] = -1;
         if (part) atomicAdd(&left, 1);
-    }
-    for (int r = threadIdx.x; r < c.n_rows; r += blockDim.x) {
-        w.row_taken[r] = 0;
-        w.row_bid[r] = kKeyInf;
     }
     __syncthreads();
     if (threadIdx.x == 0) w.info[2] = left;
@@ -534,11 +536,19 @@ __device__ __forceinline__ void greedy_commit_body(ColView c, AssocWork w) {
         } else {
             atomicAdd(&left, 1);
             w.prop_key[t] = kKeyInf;
-            w.prop_col[t] = -1;
         }
     }
     __syncthreads();
-    for (int r = threadIdx.x; r < R; r += blockDim.x) w.row_bid[r] = kKeyInf;
+    // only the rows that received a bid this round need their bid cleared (not all n_rows of them)
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const int j = w.prop_col[t];
+        if (j < 0) continue;
+        for (int k = 0; k < c.width; ++k) {
+            const int r = c.rows[(long long)k * c.stride + j];
+            if (r >= 0) w.row_bid[r] = kKeyInf;
+        }
+        w.prop_col[t] = -1;
+    }
     if (threadIdx.x == 0) w.info[2] = left;
 }
 __global__ void __launch_bounds__(1024, 1) greedy_commit_kernel(ColView c, AssocWork w) { greedy_commit_body(c, w); }
@@ -596,7 +606,7 @@ __global__ void __launch_bounds__(256) dual_loop_persistent_kernel(ColView c, As
             grid.sync();
             for (int mode = 0; mode < (it ? 2 : 1); ++mode) {
                 if (blockIdx.x == 0 && threadIdx.x == 0) w.stall_ctr[3] = mode;
-                if (blockIdx.x == 0) greedy_init_body(c, w, w.tstart);
+                greedy_init_body(c, w, w.tstart);
                 grid.sync();
                 for (int r = 0; r < kGreedyRounds; ++r) {
                     if (((volatile int *)w.info)[2] == 0) break;
@@ -693,10 +703,16 @@ __global__ void __launch_bounds__(1024, 1) active_scan_kernel(ColView c, AssocWo
     __syncthreads();
     int *cnt = w.act_tile + pick * plane;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int base = 0; base < ntiles; base += blockDim.x) {
-        const int i = base + threadIdx.x;
-        const int v = i < ntiles ? cnt[i] : 0;
-        int incl = v;
+    constexpr int kPer = 8;   // consecutive tile counts per thread (serial in registers): 8x fewer block barriers
+    for (int base = 0; base < ntiles; base += blockDim.x * kPer) {
+        const int i0 = base + threadIdx.x * kPer;
+        int v[kPer], tsum = 0;
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            v[q] = (i0 + q < ntiles) ? cnt[i0 + q] : 0;
+            tsum += v[q];
+        }
+        int incl = tsum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int tt = __shfl_up_sync(0xffffffffu, incl, o);
@@ -714,7 +730,12 @@ __global__ void __launch_bounds__(1024, 1) active_scan_kernel(ColView c, AssocWo
             wsum[lane] = ss;
         }
         __syncthreads();
-        if (i < ntiles) cnt[i] = carry + (wid ? wsum[wid - 1] : 0) + incl - v;
+        int run = carry + (wid ? wsum[wid - 1] : 0) + incl - tsum;
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            if (i0 + q < ntiles) cnt[i0 + q] = run;
+            run += v[q];
+        }
         __syncthreads();
         if (threadIdx.x == blockDim.x - 1) carry += wsum[31];
         __syncthreads();
