@@ -281,7 +281,7 @@ def main():
                     "d2h_bytes_per_step": int(infos[-1]["n_trees"] * 152 + 128)},
             "gpu_launches": None,
             "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "kernel": "gate stage (forest_count_kernel + forest_emit_kernel)",
+            "roofline": {"bound": "hbm", "kernel": "gate stage (forest_gate_kernel + forest_gate_heavy_kernel + forest_emit_kernel)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "bytes_per_launch": bytes_gate, "ms_per_launch": ms_gate},
@@ -368,13 +368,13 @@ def exchange(dist, device, t_dev, t_e2e, n_tracks):
 
 
 def launches_per_scan(d):
-    """Kernel launches of libmht_b200 per scan, counted from the launch sequence in csrc/forest.cu and
-    csrc/assoc.cu: gate 9 (live_scan, pat_table, grid_build, gate, gate_heavy, count_scan, scan_tiles, emit, tree_off) + assoc reset 1 +
-    cluster bookkeeping 5 + settle pass 7 + dual loop (ONE persistent cooperative kernel per round; with
-    sifting 3 rounds, each preceded by a pricing pass, 3 active-list kernels and a reset, plus 2 re-arms)
-    + final bound/candidates/repair 11 + track update 1."""
+    """Kernel launches of libmht_b200 per scan, counted from the ncu launch list of this round
+    (profiles/launches_r1_scan12.txt): gate 9 (live_scan, pat_table, grid_build, gate, gate_heavy, count_scan,
+    scan_tiles, emit, tree_off) + association 56 with sifting (3 rounds of pricing pass + 3 active-list kernels +
+    reset + ONE persistent cooperative dual loop, 2 re-arms, settle pass, final bound / candidates / dominance /
+    repair) or 37 without + track update 1."""
     sift = d["n_children"] > 1000000
-    return 9 + 1 + 5 + 7 + (3 * 6 + 2 if sift else 1) + 11 + 1
+    return 9 + (56 if sift else 37) + 1
 
 
 if __name__ == "__main__":

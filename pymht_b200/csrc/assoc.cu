@@ -324,7 +324,9 @@ __global__ void du_rows_kernel(ColView c, AssocWork w) { du_rows_body(c, w); }
 __device__ __forceinline__ void du_decide_body(ColView c, AssocWork w) {
     if (du_skip(c, w)) return;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
-        if (w.tstart[t] < 0 || w.uf[t] != t || w.cl_done[t]) continue;
+        if (w.tstart[t] < 0 || w.uf[t] != t) continue;
+        w.cl_flag[t] = 0;   // flags live from here to the end of the apply phase (only roots ever carry one)
+        if (w.cl_done[t]) continue;
         const double L = from_fix(w.cl_m[t] - w.cl_u[t]);
         const int nrm = w.cl_nrm[t];
         if (nrm == 0) {  // conflict-free and complementary: argmins are optimal
@@ -408,6 +410,47 @@ __device__ __forceinline__ void du_finish_body(ColView c, AssocWork w) {
 }
 __global__ void du_finish_kernel(ColView c, AssocWork w) { du_finish_body(c, w); }
 
+
+// du_apply + du_finish in ONE phase for the persistent loop (one grid barrier less per iteration).  The
+// early-out word info[0] is not read here: it is known to be 0 inside an iteration, and only the bookkeeping
+// thread below may set it, for the check at the top of the next iteration.  cl_flag is not cleared here
+// (other threads of this phase still read it): du_decide resets it for every cluster root.
+__device__ __forceinline__ void du_apply_finish_body(ColView c, AssocWork w) {
+    if (c.idx && w.act_n[2]) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) w.info[0] = 1;
+        return;
+    }
+    const int nr = *w.row_n;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += stride) {
+        const int r = w.row_list[i];
+        const int cl = w.uf[w.row_owner[r]];
+        const int fl = w.cl_flag[cl];
+        if (fl & 1) w.best_u[r] = w.u[r];
+        if (!w.cl_done[cl]) w.u[r] = fmax(0.0, w.u[r] + w.cl_step[cl] * (double)w.usage[r]);
+        w.usage[r] = 0;
+    }
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += stride) {
+        w.cl_m[t] = 0;
+        w.cl_u[t] = 0;
+        w.cl_cost[t] = 0;
+        w.cl_nrm[t] = 0;
+        if (w.tstart[t] < 0) continue;
+        const int cl = w.uf[t];
+        if (w.cl_flag[cl] & 2) w.sel[t] = w.targ[t];
+        w.tdone[t] = w.cl_done[cl];
+        w.tmin[t] = kKeyInf;
+        w.targ[t] = -1;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        w.info[1] += 1;
+        // stop when every cluster is settled, or no bound moved noticeably for kStallStop iterations
+        w.stall_ctr[0] = w.stall_ctr[2] ? 0 : w.stall_ctr[0] + 1;
+        if (w.stall_ctr[1] == 0 || w.stall_ctr[0] >= kStallStop) w.info[0] = 1;
+        w.stall_ctr[1] = 0;
+        w.stall_ctr[2] = 0;
+    }
+}
 
 static void dual_update(const ColView &c, AssocWork &w, cudaStream_t s) {
     const int tb = (c.n_trees + 127) / 128;
@@ -631,9 +674,7 @@ __global__ void __launch_bounds__(256) dual_loop_persistent_kernel(ColView c, As
         grid.sync();
         du_decide_body(c, w);
         grid.sync();
-        du_apply_body(c, w);
-        grid.sync();
-        du_finish_body(c, w);
+        du_apply_finish_body(c, w);
         grid.sync();
     }
 }
