@@ -16,6 +16,7 @@
 // in ascending measurementNumber order, the leaves of a tree are sorted lexicographically by path, so
 // N-scan pruning (Target.pruneDepth, pyTarget.py:343-356) keeps ONE contiguous range per tree found
 // by binary search -- no compaction pass, the pruned level stays in place as the node store.
+#include <algorithm>
 #include <new>
 #include <vector>
 #include <string.h>
@@ -106,6 +107,9 @@ struct mht_forest {
     void *assoc_ws;
     AssocWork aw;
     double *hist_d, *hist_h;   // history walk buffer
+    double *histb_d, *histb_h; // [kDeadChunk][kHistStride] batched walks of the tracks that died this scan
+    int *dead_d, *dead_h;      // [2][kDeadChunk] slot, position
+    std::vector<std::vector<double>> dead_hist;   // per slot: window records (leaf -> root) kept for dead tracks
     cudaStream_t stream;
     cudaEvent_t ev[6];
     // host mirrors
@@ -847,8 +851,7 @@ __global__ void track_update_kernel(UpdateArgs a) {
 
 // window part of one track's history: nodes from the root (exclusive) down to position `pos`
 constexpr int kHistRec = 24;  // doubles per history record: meas, cnllr, x[4], scan, pad, P[16]
-__global__ void history_kernel(UpdateArgs a, int t, int pos, int scan_from, double *out) {
-    if (threadIdx.x || blockIdx.x) return;
+__device__ void history_walk(const UpdateArgs &a, int t, int pos, int scan_from, double *out) {
     int n = 0;
     const int root = a.ts.root_scan[t];
     // covariances along the path: the chain from the root covariance over the leaf's hit/miss bits
@@ -870,6 +873,19 @@ __global__ void history_kernel(UpdateArgs a, int t, int pos, int scan_from, doub
         pos = L.par_lo[t] + (L.pidx[pos] - L.par_off[t]);
     }
     out[0] = (double)n;
+}
+
+__global__ void history_kernel(UpdateArgs a, int t, int pos, int scan_from, double *out) {
+    if (threadIdx.x || blockIdx.x) return;
+    history_walk(a, t, pos, scan_from, out);
+}
+// the same walk for every track that died this scan (one thread each): their window nodes leave the device
+// store with the next scans, so the host keeps the records (mht_forest_history serves them from there)
+constexpr int kHistStride = kHistRec * (MHT_MAX_WINDOW + 4);
+constexpr int kDeadChunk = 256;
+__global__ void history_batch_kernel(UpdateArgs a, const int *slot_pos, int n, int scan_from, double *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) history_walk(a, slot_pos[i], slot_pos[kDeadChunk + i], scan_from, out + (size_t)i * kHistStride);
 }
 
 // smallest distance from (px,py) to the position of any live leaf (Target.haveNoNeightbours,
@@ -966,6 +982,8 @@ static int forest_layout(mht_forest *f, bool commit) {
     f->z_d = carve<double>(p, 2 * (int64_t)f->cfg.max_meas);
     f->used_d = carve<unsigned char>(p, f->cfg.max_meas);
     f->hist_d = carve<double>(p, kHistRec * (MHT_MAX_WINDOW + 4));
+    f->histb_d = carve<double>(p, (int64_t)256 * kHistRec * (MHT_MAX_WINDOW + 4));
+    f->dead_d = carve<int>(p, 2 * 256);
     const int64_t n_rows = (int64_t)f->W * f->cfg.max_meas;
     const int64_t cap_cand = cn < (int64_t)T * 256 ? cn : (int64_t)T * 256;
     f->assoc_ws = p;
@@ -1197,6 +1215,31 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
         }
     }
     f->h_level_nodes = st.n_children;
+    {   // tracks that died this scan: keep their window records on the host
+        std::vector<int> dead;
+        for (int t : f->last_tracks)
+            if (f->out_h.status[t] > 0 && f->h_last_pos[t] >= 0 && f->scan > f->h_root_scan[t]) dead.push_back(t);
+        UpdateArgs ub;
+        if (!dead.empty()) fill_update_args(f, &ub);
+        for (size_t lo = 0; lo < dead.size(); lo += kDeadChunk) {
+            const int n = (int)std::min<size_t>(kDeadChunk, dead.size() - lo);
+            for (int i = 0; i < n; ++i) {
+                f->dead_h[i] = dead[lo + i];
+                f->dead_h[kDeadChunk + i] = f->h_last_pos[dead[lo + i]];
+            }
+            MHT_CUDA(cudaMemcpyAsync(f->dead_d, f->dead_h, sizeof(int) * 2 * kDeadChunk, cudaMemcpyHostToDevice, s));
+            history_batch_kernel<<<(n + 63) / 64, 64, 0, s>>>(ub, f->dead_d, n, f->scan, f->histb_d);
+            MHT_CUDA(cudaGetLastError());
+            MHT_CUDA(cudaMemcpyAsync(f->histb_h, f->histb_d, sizeof(double) * (size_t)n * kHistStride,
+                                     cudaMemcpyDeviceToHost, s));
+            MHT_CUDA(cudaStreamSynchronize(s));
+            for (int i = 0; i < n; ++i) {
+                const double *o = f->histb_h + (size_t)i * kHistStride;
+                const int wn = (int)o[0];
+                f->dead_hist[dead[lo + i]].assign(o, o + kHistRec * (wn + 1));
+            }
+        }
+    }
     if (info) {
         memset(info, 0, sizeof(*info));
         info->n_parents = st.n_parents;
@@ -1284,6 +1327,8 @@ extern "C" int mht_forest_create(const mht_forest_config *cfg, mht_forest **out)
     if (e == cudaSuccess) e = cudaMallocHost(&f->z_h, 16 * (size_t)cfg->max_meas);
     if (e == cudaSuccess) e = cudaMallocHost(&f->used_h, (size_t)cfg->max_meas);
     if (e == cudaSuccess) e = cudaMallocHost(&f->hist_h, kHistRec * sizeof(double) * (MHT_MAX_WINDOW + 4));
+    if (e == cudaSuccess) e = cudaMallocHost(&f->histb_h, sizeof(double) * 256 * kHistRec * (MHT_MAX_WINDOW + 4));
+    if (e == cudaSuccess) e = cudaMallocHost(&f->dead_h, sizeof(int) * 2 * 256);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&f->ev[i]);
     if (e == cudaSuccess)
@@ -1308,6 +1353,7 @@ extern "C" int mht_forest_create(const mht_forest_config *cfg, mht_forest **out)
     f->h_init_scan.assign(T, 0);
     f->h_last_pos.assign(T, -1);
     f->trunk.resize(T);
+    f->dead_hist.resize(T);
     f->h_level_nodes = 0;
     *out = f;
     return MHT_OK;
@@ -1323,6 +1369,8 @@ extern "C" void mht_forest_destroy(mht_forest *f) {
     cudaFreeHost(f->z_h);
     cudaFreeHost(f->used_h);
     cudaFreeHost(f->hist_h);
+    cudaFreeHost(f->histb_h);
+    cudaFreeHost(f->dead_h);
     cudaFree(f->arena);
     delete f;
 }
@@ -1509,7 +1557,11 @@ extern "C" int mht_forest_history(mht_forest *f, int32_t slot, int32_t cap, int3
     }
     const std::vector<TrunkNode> &tr = f->trunk[slot];
     int wn = 0;
-    if (f->h_last_pos[slot] >= 0 && f->scan > f->h_root_scan[slot]) {
+    const bool cached = !f->h_alive[slot] && !f->dead_hist[slot].empty();
+    if (cached) {
+        memcpy(f->hist_h, f->dead_hist[slot].data(), sizeof(double) * f->dead_hist[slot].size());
+        wn = (int)f->hist_h[0];
+    } else if (f->h_last_pos[slot] >= 0 && f->scan > f->h_root_scan[slot]) {
         UpdateArgs u;
         fill_update_args(f, &u);
         history_kernel<<<1, 1, 0, f->stream>>>(u, slot, f->h_last_pos[slot], f->scan, f->hist_d);

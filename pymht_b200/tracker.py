@@ -187,8 +187,8 @@ class Tracker:
         """Selected hypothesis per track (tracker.py:228-236), termination (tracker.py:252-253).
 
         The per-track arrays are read back every scan; the `Target` objects for live tracks are built
-        lazily by getTrackNodes() (terminated tracks are materialised at once, history included, because
-        their window nodes leave the device store)."""
+        lazily by getTrackNodes(); terminated tracks keep a lazy parent chain too (the library copies the window
+        records of the tracks that die in a scan to the host in one batched walk)."""
         cap = max(len(self._slots), 1)
         n = C.c_int32()
         slot = np.zeros(cap, dtype=np.int32)
@@ -204,9 +204,9 @@ class Tracker:
         self._last = (scanList, len(self.__scanHistory__), x, P, cn, meas, status)
         dead = np.flatnonzero(status[:k] != 0)
         for i in dead:
-            node = self._make_node(int(i), self._slots[i])
-            _ = node.parent          # materialise the history while the window is still on the device
-            self.__terminatedTargets__.append(node)
+            # the library keeps the window records of a track that died (mht_forest_history serves them from
+            # the host), so a terminated track's parent chain stays lazy like a live one's
+            self.__terminatedTargets__.append(self._make_node(int(i), self._slots[i], dead=True))
         if len(dead):
             keep = [i for i in range(k) if status[i] == 0]
             self._slots = [self._slots[i] for i in keep]
@@ -217,14 +217,14 @@ class Tracker:
             self._live_rows = None
         self.__trackNodes__ = None       # built on demand
 
-    def _make_node(self, row, slot):
+    def _make_node(self, row, slot, dead=False):
         scanList, scanNumber, x, P, cn, meas, status = self._last
         root = self._slot_info[slot]
         m = int(meas[row])
         return Target(scanList.time, scanNumber, x[row].copy(), P[row].copy(), ID=root.ID, P_d=root.P_d,
                       measurementNumber=m, measurement=(np.asarray(scanList.measurements)[m - 1] if m > 0 else None),
                       cumulativeNLLR=float(cn[row]), status=STATUS_TAGS[int(status[row])],
-                      parent_loader=self._make_parent_loader(slot))
+                      parent_loader=self._make_parent_loader(slot, dead))
 
     def _history(self, slot):
         cap = 64
@@ -243,11 +243,11 @@ class Tracker:
             k = n.value
             return meas[:k], x[:k], cn[:k], P[:k]
 
-    def _make_parent_loader(self, slot):
+    def _make_parent_loader(self, slot, dead=False):
         scan_at_creation = len(self.__scanHistory__)
 
         def load(leaf):
-            if len(self.__scanHistory__) != scan_at_creation:
+            if not dead and len(self.__scanHistory__) != scan_at_creation:
                 raise RuntimeError("Target.parent must be materialised before the next scan is added "
                                    "(the window nodes live on the device)")
             meas, x, cn, P = self._history(slot)

@@ -394,3 +394,31 @@ def test_every_leaf_through_the_warp_per_leaf_gate():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "3 passed" in r.stdout
+
+
+def test_terminated_tracks_keep_their_history():
+    """A track that dies keeps its full parent chain available AFTER later scans (the window nodes leave the
+    device store; the library copies the records of dying tracks to the host in one batched walk): the chain
+    must extend the reference's history of that track from the scan before it died (outside the N-scan window,
+    inside which the selected hypothesis may still have switched)."""
+    from pymht_b200.tracker import backtrackMeasurementNumbers
+    prev, seen_dead, trk_ref = {}, 0, None
+    for k, g, pre, trk, nodes, hist, info in _replay_tracker("cfg2"):
+        trk_ref = trk
+        for t in trk.__terminatedTargets__[seen_dead:]:
+            t._died_after = dict(prev)
+        seen_dead = len(trk.__terminatedTargets__)
+        prev = {int(i): [int(v) for v in h[h >= 0]] for i, h in zip(g[pre + "ids"], g[pre + "hist"])}
+        if k == int(g["n_scans"]) - 1:      # only now touch the chains of everything that died along the way
+            assert seen_dead > 0
+            for t in trk.__terminatedTargets__:
+                h = backtrackMeasurementNumbers([t])[0]
+                want = t._died_after.get(t.ID, [])
+                # the hypothesis may still switch inside the N-scan window; everything older is fixed
+                fixed = max(0, len(h) - 1 - int(g["params"][3]))
+                assert h[:fixed] == want[:fixed] and len(h) == len(want) + 1, (t.ID, h, want)
+                assert h[-1] == t.measurementNumber
+                n, depth = t, 0
+                while n.parent is not None:
+                    n, depth = n.parent, depth + 1
+                assert depth == len(h) and n.scanNumber + depth == t.scanNumber
