@@ -13,6 +13,7 @@ The M-of-N initiator is out of scope: `self.initiator` defaults to a null object
 processMeasurements(unusedRadar, unusedAis) -> [Target] can be plugged in (tracker.py:266-277).
 """
 import ctypes as C
+import os
 import time
 
 import numpy as np
@@ -72,7 +73,7 @@ class Tracker:
         self.maxMeasurements = int(kwargs.get("maxMeasurements", 65536))
         self.maxNodes = int(kwargs.get("maxNodes", 1 << 22))
         self.maxParents = int(kwargs.get("maxParents", max(1 << 16, self.maxNodes // 3)))
-        self.maxDualIterations = int(kwargs.get("maxDualIterations", 120))
+        self.maxDualIterations = int(kwargs.get("maxDualIterations", os.environ.get("MHT_DUAL_ITERS", 120)))
         self._lib = _lib.load()
         self._forest = None
         self._slots = []                    # forest slot of each live track (list order = reference order)

@@ -21,9 +21,11 @@ for k in range(upto):
     trk._grow(g[pre + "z"], float(g[pre + "time"]), trk.n_scans)
     cls = trk._cluster()
     if k == upto - 1:
-        tot_lp = tot_ip = 0.0
+        tot_lp = tot_ip = singles = 0.0
         for cl in cls:
             if len(cl) < 2:
+                t = cl[0]
+                singles += min(l.cnllr for l in trk.leaves[t]) - trk.roots[t].cnllr
                 continue
             cost, ct, ptr, idx, nr, nodes = trk._columns(cl)
             cost = cost * trk.N
@@ -42,6 +44,7 @@ for k in range(upto):
                 print("cluster trees=%d cols=%d rows=%d  LP=%.6f IP=%.6f gap=%.2e fractional=%d  (lp %.2fs, mip %.2fs)" % (
                     len(cl), n, nr, lp.fun, obj, obj - lp.fun, frac, t1 - t0, t2 - t1))
         print("sum over multi clusters: LP %.6f IP %.6f" % (tot_lp, tot_ip))
+        print("whole scan (singletons %.6f): LP bound %.6f, optimum %.6f" % (singles, singles + tot_lp, singles + tot_ip))
     trk._select(cls)
     trk._terminate()
     trk._prune()
