@@ -201,7 +201,7 @@ def test_tracker_replays_reference_golden(name):
 def test_tracker_cfg3_vs_reference(name):
     """1k targets: the scans the reference can still finish (cfg3_head: 5k measurements, lambda=1e-3, 2 scans;
     cfg3_lowclutter: lambda=1e-4, 3 scans).  While every solve is certified the tracks must be IDENTICAL to the
-    reference's.  From the first uncertified scan on (a >100-tree cluster with an LP gap: the depth-first
+    reference's (cfg3_head scan 1, cfg3_lowclutter scans 1-2: the 285-tree cluster of scan 2 is solved exactly).  From the first uncertified scan on (a >100-tree cluster with an LP gap: the depth-first
     repair gives up) the selection is a feasible near-optimum: >= 94 % of the common tracks
     still carry the reference's measurement history, <= 2 % of the tracks differ in termination, and the
     objective stays within 0.5 % of the certified lower bound."""
@@ -217,6 +217,8 @@ def test_tracker_cfg3_vs_reference(name):
                                                            "lower_bound", "objective", "ms_gate", "ms_assoc")})
         print("  identical measurement histories: %d / %d common tracks (%d ours, %d reference)" % (
             same, len(common), len(ids), len(want)))
+        if name == "cfg3_lowclutter" and k < 2:
+            assert certified_so_far, (name, k, info)
         if certified_so_far:
             assert ids == want
             assert same == len(want)
