@@ -1153,6 +1153,229 @@ __global__ void __launch_bounds__(1024, 1) comp_build_kernel(ColView c, AssocWor
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Parallel local search on the incumbent, BEFORE the candidate lists are cut (so it also runs when those
+// overflow: the giant clusters, where the greedy primal alone is tens of NLLR units above the optimum).
+// Every tree has a shortlist of kLsK columns (per-lane minima of its reduced costs at the final multipliers +
+// incumbent + all-miss leaf).  Round: (1) one warp per tree evaluates, lane = shortlisted column, the move
+// "take this column; the at most ONE tree it collides with moves to its best shortlisted column that is free
+// afterwards" and proposes the best improving one, bidding (cost change, tree) on the trees and rows it would
+// touch; (2) proposals that hold the lowest bid everywhere are applied -- they are disjoint by construction;
+// (3) bids are cleared.  Deterministic: bids are atomicMin keys.
+// ------------------------------------------------------------------------------------------------
+__global__ void ls_begin_kernel(ColView c, AssocWork w, const int *tstart) {
+    const int T = c.n_trees;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+        w.ls_tbid[t] = kKeyInf;
+        w.ls_j[t] = -1;
+        if (tstart[t] < 0) continue;
+        const int j = w.sel[t];
+        if (j < 0) {
+            w.ls_ctr[2] = 1;   // no feasible incumbent: nothing to improve on
+            continue;
+        }
+        for (int k = 0; k < c.width; ++k) {
+            const int r = c.rows[(long long)k * c.stride + j];
+            if (r >= 0) w.row_holder[r] = t;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) w.ls_ctr[0] = w.ls_ctr[1] = 0;
+}
+
+// one CTA per tree: thread i scans columns tstart + i, + 256, ...; the 8 warps' minima of each lane class
+// (column index mod 32) are combined in shared memory
+__global__ void __launch_bounds__(256) ls_shortlist_kernel(ColView c, AssocWork w, const int *tstart, const int *tend) {
+    __shared__ double s_v[8][32];
+    __shared__ int s_j[8][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int t = blockIdx.x; t < c.n_trees; t += gridDim.x) {
+        int best = -1;
+        double bv = 1e300;
+        if (tstart[t] >= 0 && !w.cl_done[w.uf[t]])
+            for (int j = tstart[t] + threadIdx.x; j < tend[t]; j += 256) {
+                const double v = w.rc[j];
+                if (v <= bv) {   // ties: the later leaf, like everywhere else
+                    bv = v;
+                    best = j;
+                }
+            }
+        s_v[wid][lane] = bv;
+        s_j[wid][lane] = best;
+        __syncthreads();
+        if (wid == 0) {
+            for (int k = 1; k < 8; ++k) {
+                const double v = s_v[k][lane];
+                const int j = s_j[k][lane];
+                if (j >= 0 && (best < 0 || v < bv || (v == bv && j > best))) {
+                    bv = v;
+                    best = j;
+                }
+            }
+            w.ls_short[t * kLsK + lane] = best;
+            if (lane == 0) {
+                w.ls_short[t * kLsK + 32] = tstart[t] >= 0 ? w.sel[t] : -1;
+                w.ls_short[t * kLsK + 33] = tstart[t];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ bool col_uses_row(const ColView &c, int j, int r) {
+    for (int k = 0; k < c.width; ++k)
+        if (c.rows[(long long)k * c.stride + j] == r) return true;
+    return false;
+}
+
+__global__ void __launch_bounds__(256) ls_propose_kernel(ColView c, AssocWork w, const int *tstart) {
+    if (w.ls_ctr[2]) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (int t = warp; t < c.n_trees; t += nwarp) {
+        if (tstart[t] < 0 || w.cl_done[w.uf[t]]) continue;
+        const int cur = w.sel[t];
+        const double cur_cost = col_cost(c, cur, t);
+        double bd = 0.0;
+        int bj = -1, bo = -1, bjo = -1;
+        for (int q = lane; q < kLsK; q += 32) {
+            const int j = w.ls_short[t * kLsK + q];
+            if (j < 0 || j == cur) continue;
+            double delta = col_cost(c, j, t) - cur_cost;
+            int other = -1, nother = 0;
+            for (int k = 0; k < c.width && nother < 2; ++k) {
+                const int r = c.rows[(long long)k * c.stride + j];
+                if (r < 0) continue;
+                const int h = w.row_holder[r];
+                if (h >= 0 && h != t && h != other) {
+                    other = h;
+                    ++nother;
+                }
+            }
+            if (nother > 1) continue;
+            int jo = -1;
+            if (nother == 1) {
+                const double cur2 = col_cost(c, w.sel[other], other);
+                double best2 = 1e300;
+                for (int q2 = 0; q2 < kLsK; ++q2) {
+                    const int cand = w.ls_short[other * kLsK + q2];
+                    if (cand < 0 || cand == w.sel[other]) continue;
+                    const double cc = col_cost(c, cand, other);
+                    if (cc > best2 || (cc == best2 && cand <= jo)) continue;
+                    bool ok = true;
+                    for (int k = 0; k < c.width && ok; ++k) {
+                        const int r2 = c.rows[(long long)k * c.stride + cand];
+                        if (r2 < 0) continue;
+                        if (col_uses_row(c, j, r2)) ok = false;                      // j takes its rows
+                        const int h = w.row_holder[r2];
+                        if (h >= 0 && h != other && h != t) ok = false;              // rows t holds now are released
+                    }
+                    if (ok) {
+                        best2 = cc;
+                        jo = cand;
+                    }
+                }
+                if (jo < 0) continue;
+                delta += best2 - cur2;
+            }
+            if (delta < -1e-12 && (delta < bd || (delta == bd && j > bj))) {
+                bd = delta;
+                bj = j;
+                bo = nother ? other : -1;
+                bjo = jo;
+            }
+        }
+        // best over the lanes (lowest cost change, ties -> larger column)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+            const int oo = __shfl_xor_sync(0xffffffffu, bo, o);
+            const int ojo = __shfl_xor_sync(0xffffffffu, bjo, o);
+            if (oj >= 0 && (bj < 0 || od < bd || (od == bd && oj > bj))) {
+                bd = od;
+                bj = oj;
+                bo = oo;
+                bjo = ojo;
+            }
+        }
+        if (lane == 0) {
+            w.ls_j[t] = bj;
+            if (bj >= 0) {
+                w.ls_delta[t] = bd;
+                w.ls_o[t] = bo;
+                w.ls_jo[t] = bjo;
+                const unsigned long long bid = (f64_key(bd) & ~0xFFFFFFull) | (unsigned long long)t;
+                atomicMin(&w.ls_tbid[t], bid);
+                if (bo >= 0) atomicMin(&w.ls_tbid[bo], bid);
+                for (int k = 0; k < c.width; ++k) {
+                    const int r = c.rows[(long long)k * c.stride + bj];
+                    if (r >= 0) atomicMin(&w.row_bid[r], bid);
+                    const int r2 = bo >= 0 ? c.rows[(long long)k * c.stride + bjo] : -1;
+                    if (r2 >= 0) atomicMin(&w.row_bid[r2], bid);
+                }
+            }
+        }
+    }
+}
+
+__global__ void ls_apply_kernel(ColView c, AssocWork w) {
+    if (w.ls_ctr[2]) return;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
+        const int j = w.ls_j[t];
+        if (j < 0) continue;
+        const int o = w.ls_o[t], jo = w.ls_jo[t];
+        const unsigned long long bid = (f64_key(w.ls_delta[t]) & ~0xFFFFFFull) | (unsigned long long)t;
+        bool win = w.ls_tbid[t] == bid && (o < 0 || w.ls_tbid[o] == bid);
+        for (int k = 0; k < c.width && win; ++k) {
+            const int r = c.rows[(long long)k * c.stride + j];
+            if (r >= 0 && w.row_bid[r] != bid) win = false;
+            const int r2 = o >= 0 ? c.rows[(long long)k * c.stride + jo] : -1;
+            if (r2 >= 0 && w.row_bid[r2] != bid) win = false;
+        }
+        if (!win) continue;
+        // release the old rows of the moving trees, then take the new ones
+        for (int k = 0; k < c.width; ++k) {
+            const int r = c.rows[(long long)k * c.stride + w.sel[t]];
+            if (r >= 0) w.row_holder[r] = -1;
+            const int r2 = o >= 0 ? c.rows[(long long)k * c.stride + w.sel[o]] : -1;
+            if (r2 >= 0) w.row_holder[r2] = -1;
+        }
+        for (int k = 0; k < c.width; ++k) {
+            const int r = c.rows[(long long)k * c.stride + j];
+            if (r >= 0) w.row_holder[r] = t;
+            const int r2 = o >= 0 ? c.rows[(long long)k * c.stride + jo] : -1;
+            if (r2 >= 0) w.row_holder[r2] = o;
+        }
+        w.sel[t] = j;
+        if (o >= 0) w.sel[o] = jo;
+        atomicAdd(&w.ls_ctr[0], 1);
+    }
+}
+
+// clear this round's bids; stop when a round applied nothing
+__global__ void ls_clear_kernel(ColView c, AssocWork w) {
+    if (w.ls_ctr[2]) return;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
+        const int j = w.ls_j[t];
+        if (j < 0) continue;
+        const int o = w.ls_o[t], jo = w.ls_jo[t];
+        w.ls_tbid[t] = kKeyInf;
+        if (o >= 0) w.ls_tbid[o] = kKeyInf;
+        for (int k = 0; k < c.width; ++k) {
+            const int r = c.rows[(long long)k * c.stride + j];
+            if (r >= 0) w.row_bid[r] = kKeyInf;
+            const int r2 = o >= 0 ? c.rows[(long long)k * c.stride + jo] : -1;
+            if (r2 >= 0) w.row_bid[r2] = kKeyInf;
+        }
+    }
+}
+__global__ void ls_round_end_kernel(AssocWork w) {
+    if (w.ls_ctr[2]) return;
+    if (w.ls_ctr[0] == 0) w.ls_ctr[2] = 1;
+    w.ls_ctr[1] += w.ls_ctr[0];
+    w.ls_ctr[0] = 0;
+}
+
 // one thread per component: first-improvement local search on the incumbent over the candidate columns.
 //   1-opt: a tree switches to a cheaper candidate whose rows are free;
 //   2-opt: a tree takes a candidate that collides with exactly ONE other tree, which moves to its best
@@ -1435,6 +1658,13 @@ static int64_t carve_all(Carver &cv, int64_t cap_cols, int64_t T, int64_t R, int
     d.row_mark = cv.take<int>(R);
     d.row_cont = cv.take<int>(R);
     d.row_holder = cv.take<int>(R);
+    d.ls_short = cv.take<int>(T * kLsK);
+    d.ls_delta = cv.take<double>(T);
+    d.ls_j = cv.take<int>(T);
+    d.ls_o = cv.take<int>(T);
+    d.ls_jo = cv.take<int>(T);
+    d.ls_tbid = cv.take<unsigned long long>(T);
+    d.ls_ctr = cv.take<int>(4);
     d.row_list = cv.take<int>(R);
     d.row_n = cv.take<int>(4);
     d.cap_act = cap_cols < (1 << 20) ? cap_cols : (cap_cols / 8 > (1 << 20) ? cap_cols / 8 : (1 << 20));
@@ -1568,6 +1798,24 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
     final_prepare_kernel<<<1, 1024, 0, s>>>(c, w);
     dual_rc_kernel<true><<<grid_dim, 256, 0, s>>>(c, w);
     dual_arg_kernel<true><<<grid_dim, 256, 0, s>>>(c, w);
+    {   // parallel local search on the incumbent (see ls_propose_kernel)
+        static const int ls_rounds = getenv("MHT_LS_ROUNDS") ? atoi(getenv("MHT_LS_ROUNDS")) : 16;
+        const int tb = (c.n_trees + 127) / 128, wb = (c.n_trees + 7) / 8;
+        if (ls_rounds > 0) {
+            MHT_CUDA(cudaMemsetAsync(w.ls_ctr, 0, 4 * sizeof(int), s));
+            MHT_CUDA(cudaMemsetAsync(w.row_bid, 0xff, sizeof(unsigned long long) * (size_t)c.n_rows, s));
+            ls_begin_kernel<<<tb, 128, 0, s>>>(c, w, g_tstart);
+            ls_shortlist_kernel<<<c.n_trees < 8 * kSMs ? c.n_trees : 8 * kSMs, 256, 0, s>>>(c, w, g_tstart, g_tend);
+            for (int round = 0; round < ls_rounds; ++round) {
+                ls_propose_kernel<<<wb, 256, 0, s>>>(c, w, g_tstart);
+                ls_apply_kernel<<<tb, 128, 0, s>>>(c, w);
+                ls_clear_kernel<<<tb, 128, 0, s>>>(c, w);
+                ls_round_end_kernel<<<1, 1, 0, s>>>(w);
+            }
+            // the candidate-based search below keeps its own holder table
+            MHT_CUDA(cudaMemsetAsync(w.row_holder, 0xff, sizeof(int) * (size_t)c.n_rows, s));
+        }
+    }
     final_bound_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
     cand_count_kernel<<<grid_dim, 256, 0, s>>>(c, w);
     cand_scan_kernel<<<1, 1024, 0, s>>>(c, w);

@@ -6,6 +6,7 @@
 namespace mht {
 
 constexpr int kAssocInfo = 16;  // ints in AssocWork::info
+constexpr int kLsK = 34;        // shortlist: 32 per-lane minima + incumbent + all-miss leaf
 
 // Column view: one column = one leaf hypothesis.  Columns of a tree are contiguous.
 struct ColView {
@@ -54,6 +55,11 @@ struct AssocWork {
     int *row_mark;
     int *row_cont;             // [R] 1 = candidates of two or more trees use the row
     int *row_holder;           // [R] local search: tree currently using the row (-1 free)
+    int *ls_short;             // [T][kLsK] shortlist of columns per tree (parallel local search)
+    double *ls_delta;          // [T] proposed move: cost change ...
+    int *ls_j, *ls_o, *ls_jo;  // [T] ... own new column, displaced tree (-1 none) and its new column
+    unsigned long long *ls_tbid;   // [T] bids on trees
+    int *ls_ctr;               // [4] moves applied this round / total, stop flag
     int *row_list;             // [R] rows touched by at least one column (order irrelevant)
     int *row_n;                // device: entries of row_list
     int *tstart;               // [T] first column of each tree (-1: the tree has no columns)
