@@ -1799,7 +1799,7 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
     dual_rc_kernel<true><<<grid_dim, 256, 0, s>>>(c, w);
     dual_arg_kernel<true><<<grid_dim, 256, 0, s>>>(c, w);
     {   // parallel local search on the incumbent (see ls_propose_kernel)
-        static const int ls_rounds = getenv("MHT_LS_ROUNDS") ? atoi(getenv("MHT_LS_ROUNDS")) : 16;
+        static const int ls_rounds = getenv("MHT_LS_ROUNDS") ? atoi(getenv("MHT_LS_ROUNDS")) : 10;
         const int tb = (c.n_trees + 127) / 128, wb = (c.n_trees + 7) / 8;
         if (ls_rounds > 0) {
             MHT_CUDA(cudaMemsetAsync(w.ls_ctr, 0, 4 * sizeof(int), s));
