@@ -181,7 +181,27 @@ def cpu_sample_text(kind, times, leaves):
                 else "oracle port of the reference", len(times), leaves, [round(t, 2) for t in times]))
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that writes to file descriptor 1 (NCCL's version banner,
+    library prints of the reference arm) is sent to stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
@@ -215,7 +235,7 @@ def main():
                 "cpu_baseline": {"value": v, "unit": "scans/s", "cores": 1, "kind": kind,
                                  "sample": cpu_sample_text(kind, times, leaves)},
                 "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -225,8 +245,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: one JSON line only
+        # NCCL writes its version banner / debug lines to stdout by default: send them to stderr so that stdout
+        # carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     preroll = N + 2
     n_scans = preroll + args.warmup + args.steps
@@ -300,7 +321,7 @@ def main():
                                     "sample": cpu_sample_text(kind, times, leaves) +
                                     "; the GPU figure is at steady state (%.2e live leaves per scan)"
                                     % line["scan_stats"]["n_parents"]}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -349,7 +370,7 @@ def run_tree_sharded(args, name, config, dist, torch, rank, world, local_rank, p
                              "bytes_gathered_per_scan": float(np.mean([d["bytes_gathered"] for d in log]))},
                 "scan_stats": {"tracks": n_tracks, "objective": float(np.mean([d["objective"] for d in infos])),
                                "lower_bound": float(np.mean([d["lower_bound"] for d in infos]))}}
-        print(json.dumps(line))
+        emit(line)
     trk.close()
     dist.destroy_process_group()
 

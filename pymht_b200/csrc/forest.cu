@@ -192,10 +192,14 @@ __global__ void __launch_bounds__(1024, 1) live_scan_kernel(ScanArgs a) {
         a.cur.par_lo[t] = a.ts.live_lo[t];
         const int len = a.ts.alive[t] ? a.ts.live_hi[t] - a.ts.live_lo[t] : 0;
         // tiles whose first live leaf belongs to this tree (the gate kernels start their tree search here)
-        for (int k = (acc + kTile - 1) / kTile; (long long)k * kTile < (long long)acc + len; ++k) a.tile_tree[k] = t;
+        // (nothing past the table when the live leaves exceed max_parents: the scan is refused anyway)
+        const int k_max = (int)(a.cap_par / kTile) + 2;
+        for (int k = (acc + kTile - 1) / kTile; (long long)k * kTile < (long long)acc + len && k <= k_max; ++k)
+            a.tile_tree[k] = t;
         acc += len;
     }
-    if (threadIdx.x == 0) a.tile_tree[(*a.d_np + kTile - 1) / kTile] = T - 1;   // sentinel for the last tile
+    if (threadIdx.x == 0)   // sentinel for the last tile
+        a.tile_tree[min((*a.d_np + kTile - 1) / kTile, (int)(a.cap_par / kTile) + 3)] = T - 1;
 }
 
 // live index -> (tree, position in the previous level): largest t in [t_lo, t_hi] with par_off[t] <= i.

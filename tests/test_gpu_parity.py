@@ -313,6 +313,15 @@ def test_capacity_errors_are_loud_and_leave_the_forest_usable():
     trk.addMeasurementList(MeasurementList(2.5, z[:5]))   # still usable afterwards
     assert len(trk.getTrackNodes()) == 1 and trk.scanInfo[-1]["n_children"] == 6
     trk.close()
+    # more live leaves than max_parents: refused at the start of the next scan, nothing is written out of bounds
+    trk, pv = _small_tracker(N=5, maxNodes=1 << 12, maxParents=16, maxMeasurements=64)
+    trk.initiateTarget(Target(0.0, None, np.array([0.0, 0.0, 0.0, 0.0]), pv.P0))
+    z = np.random.RandomState(1).normal(scale=1.0, size=(30, 2)).astype(np.float32)
+    trk.addMeasurementList(MeasurementList(2.5, z))        # 31 children from 1 parent: fine
+    with pytest.raises(_lib.MhtError) as e:               # 31 live leaves > 16
+        trk.addMeasurementList(MeasurementList(5.0, z))
+    assert e.value.code == _lib.MHT_E_CAPACITY and "live leaves" in str(e.value)
+    trk.close()
 
 
 def test_initiate_target_respects_merge_threshold():
