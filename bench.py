@@ -390,12 +390,14 @@ def exchange(dist, device, t_dev, t_e2e, n_tracks):
 
 def launches_per_scan(d):
     """Kernel launches of libmht_b200 per scan, counted from the ncu launch list of this round
-    (profiles/launches_r1_scan12.txt): gate 9 (live_scan, pat_table, grid_build, gate, gate_heavy, count_scan,
-    scan_tiles, emit, tree_off) + association 98 with sifting (3 rounds of pricing pass + 3 active-list kernels +
-    reset + ONE persistent cooperative dual loop, 2 re-arms, settle pass, parallel local search 2 + 10 rounds x 4,
-    final bound / candidates / dominance / repair) or 79 without + track update 1."""
+    (profiles/launches_r1_scan12.txt, taken with 3 sifting rounds = 109 launches): gate 9 (live_scan, pat_table,
+    grid_build, gate, gate_heavy, count_scan, scan_tiles, emit, tree_off) + association with sifting (per round:
+    pricing pass + 3 active-list kernels + reset + ONE persistent cooperative dual loop + re-arm = 7; settle pass,
+    parallel local search 2 + 10 rounds x 4, final bound / candidates / dominance / repair = 78) or 79 without +
+    track update 1 + batched history walk of dying tracks 1."""
     sift = d["n_children"] > 1000000
-    return 9 + (98 if sift else 79) + 1
+    rounds = int(os.environ.get("MHT_SIFT_ROUNDS", "2"))
+    return 9 + (78 + 7 * rounds - 1 if sift else 79) + 1 + 1
 
 
 if __name__ == "__main__":
