@@ -54,6 +54,21 @@ def _scenario(name):
             a = rng.uniform(0, 2 * np.pi)
             xs.append([p[0], p[1], 5 * np.cos(a), 5 * np.sin(a)])
         return np.array(xs), 10, 900.0, 1e-4, 5, 0.9, 77
+    if name == "cfg5_n8":
+        # the same crossing layout with BASELINE config 5's window N=8 (W = 9 path planes: the wide emit kernel)
+        # and enough scans for the window to fill and the N-scan pruning to run
+        xs = []
+        for k in range(6):
+            c = rng.uniform(-500, 500, size=2)
+            v = 8.0
+            tc = 4 * T_RADAR
+            xs.append([c[0] - v * tc, c[1] + 3.0, v, 0.0])
+            xs.append([c[0] + 2.0, c[1] - v * tc, 0.0, v])
+        for k in range(12):
+            p = rng.uniform(-600, 600, size=2)
+            a = rng.uniform(0, 2 * np.pi)
+            xs.append([p[0], p[1], 5 * np.cos(a), 5 * np.sin(a)])
+        return np.array(xs), 12, 900.0, 1e-4, 8, 0.9, 78
     raise KeyError(name)
 
 

@@ -176,7 +176,7 @@ def _replay_tracker(name, n_scans=None, **kw):
     trk.close()
 
 
-@pytest.mark.parametrize("name", ["cfg1_crossing", "cfg2_small", "cfg5_small", "cfg2"])
+@pytest.mark.parametrize("name", ["cfg1_crossing", "cfg2_small", "cfg5_small", "cfg2", "cfg5_n8"])
 def test_tracker_replays_reference_golden(name):
     """Whole addMeasurementList sequences against what the unmodified reference produced."""
     for k, g, pre, trk, nodes, hist, info in _replay_tracker(name):

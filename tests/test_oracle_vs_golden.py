@@ -76,6 +76,11 @@ def test_replay_small(name):
     replay(name)
 
 
+def test_replay_cfg5_n8():
+    """BASELINE config 5's window (N = 8) on the crossing layout: the window fills at scan 8, then N-scan pruning runs."""
+    replay("cfg5_n8", n_scans=9)
+
+
 def test_replay_cfg2():
     replay("cfg2", n_scans=6)
 
