@@ -9,10 +9,13 @@ pre-rolled N+2 scans so the hypothesis trees have reached their windowed size).
   value : device-timed (CUDA events on the forest's stream, inside libmht_b200), scan already in HBM
   e2e   : same scans through pymht_b200.Tracker.addMeasurementList with HOST measurement arrays
           (H2D of the scan and D2H of the per-track results inside the timed region), wall clock
-  --impl reference : the oracle port of the reference's CPU path (oracle/mht_oracle.py; the reference
-          itself is pure Python and cannot travel to the GPU box) on a bounded sample.
-N > 1: every rank owns one independent surveillance sector (its own 1k-target forest, weak scaling);
-the only exchange is an all_gather of the per-rank track summaries.
+  --impl reference : the reference's own CPU path -- the UNMODIFIED reference installed at baseline/_ref when it is
+          there (driven through its public API under oracle/ref_shim.py), else the oracle port
+          (oracle/mht_oracle.py) -- on a bounded sample (the first scans of the same scenario).
+N > 1: by default every rank owns one independent surveillance sector (its own 1k-target forest, weak scaling);
+the only exchange is an all_gather of the per-rank track summaries.  `--shard trees` instead shards the trees of
+ONE region over the ranks and all-gathers the column records of the 0/1 program (pymht_b200/sharded.py).
+stdout carries exactly one JSON line; everything else goes to stderr.
 """
 import argparse
 import ctypes as C
