@@ -18,6 +18,7 @@ for j in sel_opt: sel_inc[ct[j]] = j
 iters_node = int(args[2]) if len(args) > 2 else 40
 slacks = [float(v) for v in args[3].split(",")] if len(args) > 3 else [0.76, 5.0]
 max_nodes = int(args[4]) if len(args) > 4 else 200000
+max_depth = int(args[5]) if len(args) > 5 else 60
 for slack, label in [(v, "incumbent %.2f above the optimum" % v) for v in slacks]:
     best_sel = np.zeros(nT, dtype=np.int32); best = C.c_double(); nodes = C.c_int()
     cst = np.ascontiguousarray(cost, dtype=np.float64); tr = np.ascontiguousarray(ct, dtype=np.int32)
@@ -26,7 +27,7 @@ for slack, label in [(v, "incumbent %.2f above the optimum" % v) for v in slacks
     t0 = time.time()
     lib.lbb_solve_host.argtypes = [C.c_int] * 4 + [C.c_void_p] * 4 + [C.c_double, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     proven = lib.lbb_solve_host(n, nT, nr, W, p(cst), p(tr), p(np.ascontiguousarray(RM)), p(u0), float(opt + slack), p(sel_inc),
-                                200, iters_node, max_nodes, 60, p(best_sel), C.byref(best), C.byref(nodes))
+                                200, iters_node, max_nodes, max_depth, p(best_sel), C.byref(best), C.byref(nodes))
     ok = abs(best.value - opt) < 1e-9
     taken = RM[:, best_sel][RM[:, best_sel] >= 0]
     feas = len(taken) == len(set(taken.tolist())) and list(ct[best_sel]) == list(range(nT))
