@@ -181,6 +181,8 @@ class Tracker:
         for k, v in self.runtimeLog.items():
             if k in self.toc:
                 v.append(self.toc[k])
+        if kwargs.get("checkIntegrity", False):      # reference tracker.py:261-262
+            self._checkTrackerIntegrity()
         if kwargs.get("printTime", False):
             print(self.getTimeLogString())
 
