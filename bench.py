@@ -39,10 +39,41 @@ WORKLOADS = {
 T_RADAR = 2.5
 
 
+SCENARIO_SOURCE = "pymht_b200.utils.simulator (own generator)"
+
+
 def make_scenario(name, n_scans, seed_offset=0):
+    """Scans of the named workload.  BASELINE.md section 3: the reference's own simulator (seed_simulator(seed) ->
+    generateInitialTargets -> simulateTargets -> simulateScans, pymht/utils/simulator.py:15-110), taken from the
+    UNMODIFIED reference installed at baseline/_ref when it is there (same scans for both arms); the repo's own
+    generator otherwise.  Returned in this repo's container classes."""
+    global SCENARIO_SOURCE
+    nT, R, lam, N, Pd, seed, _, _ = WORKLOADS[name]
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref_root, "pymht")) and not os.environ.get("MHT_BENCH_OWN_SIM"):
+        os.environ["PYMHT_REFERENCE_ROOT"] = ref_root
+        from oracle import ref_shim          # input generation only: nothing timed runs through oracle/
+        ref_shim.install()
+        import pymht.utils.simulator as rsim
+        import pymht.models.pv as rpv
+        from pymht_b200.utils.classDefinitions import MeasurementList, ScanList, SimList, SimTargetCartesian
+        rsim.seed_simulator(seed + seed_offset)
+        p0 = np.zeros(2)
+        init = rsim.generateInitialTargets(nT, p0, R, Pd, rpv.sigmaQ_true)
+        rl = rsim.simulateTargets(init, n_scans * T_RADAR, T_RADAR, rpv)
+        rscans = rsim.simulateScans(rl, T_RADAR, rpv.C_RADAR, rpv.R_RADAR(rpv.sigmaR_RADAR_true), lam, R, p0,
+                                    shuffle=True, localClutter=False, globalClutter=True, preInitialized=True)
+        simList = SimList()
+        for step in rl:
+            simList.append([SimTargetCartesian(np.asarray(t.cartesianState(), dtype=np.float64), t.time, Pd,
+                                               rpv.sigmaQ_true) for t in step])
+        scans = ScanList()
+        for sc in rscans[:n_scans]:
+            scans.append(MeasurementList(sc.time, np.asarray(sc.measurements, dtype=np.float32).reshape(-1, 2)))
+        SCENARIO_SOURCE = "reference simulator (baseline/_ref pymht/utils/simulator.py, seed %d)" % (seed + seed_offset)
+        return simList, scans
     import pymht_b200.utils.simulator as sim
     from pymht_b200.models import pv
-    nT, R, lam, N, Pd, seed, _, _ = WORKLOADS[name]
     sim.seed_simulator(seed + seed_offset)
     p0 = np.zeros(2)
     init = sim.generateInitialTargets(nT, p0, R, Pd, pv.sigmaQ_true)
@@ -114,10 +145,12 @@ def run_device_leg(name, scans, simList, preroll, warmup, steps):
     infos = []
     for k, (s, dz) in enumerate(zip(scans, d_scans)):
         info = _lib.ScanInfo()
+        l0 = int(lib.mht_launch_count())
         _lib.check(lib.mht_forest_scan_device(trk._forest, dz.shape[0], dz.data_ptr(), float(s.time), C.byref(info)),
                    allow=(_lib.MHT_E_NOTOPTIMAL,))
         d = info.as_dict()
         d["n_meas"] = int(dz.shape[0])
+        d["launches"] = int(lib.mht_launch_count()) - l0     # counted by the library at every launch site
         infos.append(d)
     timed = infos[preroll + warmup:preroll + warmup + steps]
     dev_bytes = trk.deviceBytes()
@@ -137,10 +170,10 @@ def run_e2e_leg(name, scans, simList, preroll, warmup, steps):
     h2d = int(np.mean([16 * len(s.measurements) for s in scans[preroll + warmup:]]))
     n_tracks = len(trk.getTrackNodes())
     trk.close()
-    return timed, h2d, n_tracks
+    return timed, h2d, n_tracks, t_steps
 
 
-def run_cpu_reference(name, max_scans=2):
+def run_cpu_reference(name, max_scans=2, n_scans_scenario=None):
     """The reference's own CPU path on the first scans of the same workload, cold start.
 
     Preferred: the UNMODIFIED reference installed at baseline/_ref (pip --no-deps --target, see
@@ -150,7 +183,9 @@ def run_cpu_reference(name, max_scans=2):
     oracle port (oracle/mht_oracle.py).  Returns (kind, per-scan seconds of Process+Cluster+Optim+
     Terminate+N-Prune, leaves after each scan)."""
     nT, R, lam, N, Pd, seed, _, _ = WORKLOADS[name]
-    simList, scans = make_scenario(name, max_scans)
+    # the scenario is generated at the GPU arm's length so that scans 1..max_scans are the SAME scans in both arms
+    simList, scans = make_scenario(name, n_scans_scenario or max_scans)
+    scans = scans[:max_scans]
     ref_root = os.path.join(ROOT, "baseline", "_ref")
     if os.path.isdir(os.path.join(ref_root, "pymht")):
         os.environ["PYMHT_REFERENCE_ROOT"] = ref_root
@@ -207,8 +242,8 @@ def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3_1k_targets_5k_meas_N6", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -229,8 +264,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        kind, times, leaves = run_cpu_reference(name, max_scans=2)
+        kind, times, leaves = run_cpu_reference(name, max_scans=2, n_scans_scenario=N + 2 + args.warmup + args.steps)
         v = len(times) / sum(times)
+        config["scans"] = SCENARIO_SOURCE
         line = {"metric": "scans/sec @ 1k targets, 5k meas/scan", "value": v, "unit": "scans/s", "n_gpus": args.gpus,
                 "steps": len(times), "warmup": 0, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64 state / f32 covariance", "data": "synthetic", "config": config,
@@ -268,7 +304,7 @@ def main():
     barrier()
     timed, infos, dev_bytes = run_device_leg(name, scans, simList, preroll, args.warmup, args.steps)
     barrier()
-    e2e_times, h2d, n_tracks = run_e2e_leg(name, scans, simList, preroll, args.warmup, args.steps)
+    e2e_times, h2d, n_tracks, e2e_all = run_e2e_leg(name, scans, simList, preroll, args.warmup, args.steps)
     barrier()
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -281,6 +317,7 @@ def main():
         K = len(timed)
         value = world * K / t_dev
         e2e = world * K / t_e2e
+        config["scans"] = SCENARIO_SOURCE
         ms_gate = float(np.mean([d["ms_gate"] for d in timed]))
         bytes_gate = float(np.mean([gate_bytes(d) for d in timed]))
         peaks = {}
@@ -291,11 +328,28 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = bytes_gate / (ms_gate * 1e-3) / 1e9
         traffic = None   # measured DRAM bytes of the gate stage (ncu capture in profiles/), scaled by children
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))["gate_stage"]
-            traffic = tr["dram_bytes"] / tr["n_children"] * float(np.mean([d["n_children"] for d in timed]))
-        except Exception:
-            pass
+        for fn in ("traffic_r2.json", "traffic_r1.json"):
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", fn)))["gate_stage"]
+                traffic = tr["dram_bytes"] / tr["n_children"] * float(np.mean([d["n_children"] for d in timed]))
+                break
+            except Exception:
+                pass
+
+        def pct(key, src=timed):
+            v = np.array([d[key] for d in src], dtype=np.float64)
+            return {"p50": float(np.percentile(v, 50)), "p95": float(np.percentile(v, 95)), "max": float(v.max()),
+                    "min": float(v.min()), "mean": float(v.mean())}
+
+        # ILP roofline: bytes per dual iteration = 8 nnz + 24 (cols + rows) on the columns the loop
+        # iterates on, against the measured time per iteration of the persistent dual-loop kernel
+        it_bytes = float(np.mean([8.0 * d["nnz_active"] + 24.0 * ((d["n_active"] or d["n_children"]) + d["rows_active"])
+                                  for d in timed]))
+        iters = float(np.mean([max(d["dual_iters"], 1) for d in timed]))
+        ms_dual = float(np.mean([d["ms_dual"] for d in timed]))
+        us_iter = 1e3 * ms_dual / iters
+        ilp_ach = it_bytes / (us_iter * 1e-6) / 1e9 if us_iter > 0 else 0.0
+        gaps = [d["objective"] - d["lower_bound"] for d in timed]
         line = {
             "metric": "scans/sec @ 1k targets, 5k meas/scan", "value": value, "unit": "scans/s", "n_gpus": world,
             "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True,
@@ -303,27 +357,52 @@ def main():
             "config": config,
             "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(infos[-1]["n_trees"] * 152 + 128)},
-            "gpu_launches": None,
+            "gpu_launches": int(sum(d["launches"] for d in timed)),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "gate stage (forest_gate_kernel + forest_gate_heavy_kernel + forest_emit_kernel)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "bytes_per_launch": bytes_gate, "ms_per_launch": ms_gate},
+            "roofline_ilp": {"bound": "hbm", "kernel": "dual_loop_persistent_kernel (one projected-subgradient iteration)",
+                             "bytes_per_iteration": it_bytes, "us_per_iteration": us_iter, "iterations_per_scan": iters,
+                             "ms_dual_per_scan": ms_dual, "achieved": ilp_ach, "peak": peak, "unit": "GB/s",
+                             "frac": ilp_ach / peak,
+                             "note": "latency bound (grid barriers), far from HBM: the iteration's working set is L2 resident"},
             "stage_ms": {k: float(np.mean([d[k] for d in timed])) for k in
-                         ("ms_gate", "ms_cluster", "ms_assoc", "ms_prune", "ms_total")},
+                         ("ms_gate", "ms_cluster", "ms_assoc", "ms_dual", "ms_exact", "ms_prune", "ms_total")},
+            "scan_ms": {"ms_total": pct("ms_total"), "ms_assoc": pct("ms_assoc"), "ms_gate": pct("ms_gate")},
+            "ilp": {"certified_scans": int(sum(1 for d in timed if d["certified"])), "scans": K,
+                    "gap_mean": float(np.mean(gaps)), "gap_max": float(np.max(gaps)),
+                    "gap_rel_mean": float(np.mean([g / max(abs(d["lower_bound"]), 1e-9) for g, d in zip(gaps, timed)])),
+                    "open_components_mean": float(np.mean([d["open_components"] for d in timed])),
+                    "note": "certified = the exact search proved the selection optimal; otherwise a feasible "
+                            "selection with the stated gap to the Lagrangian lower bound (the reference's CBC would "
+                            "warn 'NOT optimal' under a time limit, tracker.py:1201-1204)"},
             "scan_stats": {k: float(np.mean([d[k] for d in timed])) for k in
                            ("n_trees", "n_parents", "n_children", "n_pairs", "n_clusters", "n_multi_clusters", "dual_iters",
-                            "n_candidates", "bb_nodes", "certified", "lower_bound", "objective", "n_active")},
+                            "n_candidates", "bb_nodes", "bb_iters", "certified", "lower_bound", "objective", "n_active",
+                            "nnz_active", "rows_active")},
             "forest_hbm_bytes": dev_bytes,
         }
-        line["gpu_launches"] = int(sum(launches_per_scan(d) for d in timed))
         if not args.no_cpu_baseline:
-            kind, times, leaves = run_cpu_reference(name, max_scans=2)
+            kind, times, leaves = run_cpu_reference(name, max_scans=2, n_scans_scenario=n_scans)
             v = len(times) / sum(times)
+            # like for like: the SAME first scans from a cold start on the GPU (device-timed and end to end), with
+            # the leaf counts of both sides printed
+            cold = infos[:len(times)]
             line["cpu_baseline"] = {"value": v, "unit": "scans/s", "cores": 1, "kind": kind,
                                     "sample": cpu_sample_text(kind, times, leaves) +
-                                    "; the GPU figure is at steady state (%.2e live leaves per scan)"
+                                    "; the GPU headline is at steady state (%.2e live leaves per scan)"
                                     % line["scan_stats"]["n_parents"]}
+            line["like_for_like"] = {
+                "what": "scans 1-%d of the same scenario from a cold start, both sides" % len(times),
+                "cpu_s": [float(t) for t in times], "cpu_leaves_after_scan": [int(l) for l in leaves],
+                "gpu_ms_device": [float(d["ms_total"]) for d in cold],
+                "gpu_ms_e2e": [1e3 * float(t) for t in e2e_all[:len(times)]],
+                "gpu_leaves_after_scan": [int(d["n_children"]) for d in cold],
+                "gpu_certified": [int(d["certified"]) for d in cold],
+                "ratio_e2e": float(sum(times) / max(sum(e2e_all[:len(times)]), 1e-12)),
+                "ratio_device": float(sum(times) / max(1e-3 * sum(d["ms_total"] for d in cold), 1e-12))}
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
@@ -389,18 +468,6 @@ def exchange(dist, device, t_dev, t_e2e, n_tracks):
     gathered = [torch.zeros_like(summary) for _ in range(dist.get_world_size())]
     dist.all_gather(gathered, summary)
     return float(t[0]), float(t[1]), [int(g[0]) for g in gathered]
-
-
-def launches_per_scan(d):
-    """Kernel launches of libmht_b200 per scan, counted from the ncu launch list of this round
-    (profiles/launches_r1_scan12.txt, taken with 3 sifting rounds = 109 launches): gate 9 (live_scan, pat_table,
-    grid_build, gate, gate_heavy, count_scan, scan_tiles, emit, tree_off) + association with sifting (per round:
-    pricing pass + 3 active-list kernels + reset + ONE persistent cooperative dual loop + re-arm = 7; settle pass,
-    parallel local search 2 + 10 rounds x 4, final bound / candidates / dominance / repair = 78) or 79 without +
-    track update 1 + batched history walk of dying tracks 1."""
-    sift = d["n_children"] > 1000000
-    rounds = int(os.environ.get("MHT_SIFT_ROUNDS", "2"))
-    return 9 + (78 + 7 * rounds - 1 if sift else 79) + 1 + 1
 
 
 if __name__ == "__main__":

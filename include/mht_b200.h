@@ -49,6 +49,8 @@ int mht_version(void);
 const char *mht_last_error(void);
 /* number of visible sm_100 devices (0 => every compute entry point returns MHT_E_NODEVICE). */
 int mht_device_count(void);
+/* kernels this library has launched so far in this process (every launch site counts itself). */
+int64_t mht_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Stateless operator: replaces the body of Tracker._processLeafNodes for ANY batch of leaves
@@ -93,7 +95,8 @@ int mht_gate_batch_host(const mht_model *model, int64_t L, int64_t M, const doub
  * Tracker._solveOptimumAssociation/_solveBLP_OR_TOOLS (tracker.py:979-1217) for the rest, all
  * clusters at once:   min sum c_j tau_j ; each tree exactly one column ; each row at most once.
  * Columns of a tree must be contiguous (col_tree non-decreasing).  Lagrangian dual ascent on the
- * row constraints + reduced-cost fixing + exact depth-first repair on the surviving columns.
+ * row constraints + reduced-cost fixing + exact search on the surviving columns (enumeration for small
+ * components, best-first Lagrangian branch & bound for the rest; wall-clock budget MHT_BB_MS, default 10 s).
  * out d_selected_col[T] (column index per tree, -1 for trees without columns),
  *     h_info[8] = {lower bound, objective, n_candidate_cols, n_components, bb_nodes, dual_iters,
  *                  certified(1/0), max_component_trees}.
@@ -127,7 +130,10 @@ typedef struct mht_forest_config {
     double radar_range;      /* tracker.py:45  */
     double position[2];      /* tracker.py:44  */
     int32_t max_dual_iters;  /* Lagrangian iterations per scan        */
-    int32_t reserved;
+    int32_t exact_ms;        /* wall-clock budget (ms) per scan of the exact branch & bound that closes the
+                                components the dual loop leaves open (tracker.py:1155-1217 is an exact MILP);
+                                0 = default (20 ms), < 0 = no exact search.  A scan whose budget ran out returns
+                                a feasible selection with certified = 0 and the bound gap in mht_scan_info. */
 } mht_forest_config;
 
 /* Per-scan summary (host struct filled by mht_forest_scan). */
@@ -150,6 +156,13 @@ typedef struct mht_scan_info {
     int64_t n_active;        /* columns on the dual iteration's active list (0 = all columns iterate) */
     int32_t max_component;   /* trees in the largest component handed to the exact search */
     int32_t n_components;    /* multi-tree components handed to the exact search */
+    float ms_dual;           /* time inside the persistent dual-loop kernel launches (part of ms_assoc)      */
+    float ms_exact;          /* time of the exact repair stage: plan, compaction, branch & bound, write-back */
+    int64_t nnz_active;      /* row incidences of the columns the dual loop iterates on (its last round)     */
+    int32_t rows_active;     /* measurement rows carrying a multiplier                                        */
+    int32_t bb_iters;        /* subgradient iterations spent inside the branch & bound                        */
+    int32_t open_components; /* components whose exact search did not finish (0 when certified)               */
+    int32_t reserved;
 } mht_scan_info;
 
 int mht_forest_create(const mht_forest_config *cfg, mht_forest **out);

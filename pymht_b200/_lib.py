@@ -38,7 +38,7 @@ class ForestConfig(C.Structure):
     _fields_ = [("model", Model), ("n_scan_window", C.c_int32), ("max_trees", C.c_int32), ("max_meas", C.c_int32),
                 ("max_nodes", C.c_int64), ("max_parents", C.c_int64), ("default_Pd", C.c_double),
                 ("score_upper", C.c_double), ("cnllr_upper", C.c_double), ("radar_range", C.c_double),
-                ("position", C.c_double * 2), ("max_dual_iters", C.c_int32), ("reserved", C.c_int32)]
+                ("position", C.c_double * 2), ("max_dual_iters", C.c_int32), ("exact_ms", C.c_int32)]
 
 
 class ScanInfo(C.Structure):
@@ -47,7 +47,10 @@ class ScanInfo(C.Structure):
                 ("n_dead", C.c_int32), ("dual_iters", C.c_int32), ("certified", C.c_int32),
                 ("n_candidates", C.c_int64), ("bb_nodes", C.c_int64), ("lower_bound", C.c_double),
                 ("objective", C.c_double), ("ms_gate", C.c_float), ("ms_cluster", C.c_float),
-                ("ms_assoc", C.c_float), ("ms_prune", C.c_float), ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("n_active", C.c_int64), ("max_component", C.c_int32), ("n_components", C.c_int32)]
+                ("ms_assoc", C.c_float), ("ms_prune", C.c_float), ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("n_active", C.c_int64), ("max_component", C.c_int32), ("n_components", C.c_int32),
+                ("ms_dual", C.c_float), ("ms_exact", C.c_float), ("nnz_active", C.c_int64),
+                ("rows_active", C.c_int32), ("bb_iters", C.c_int32), ("open_components", C.c_int32),
+                ("reserved", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -58,6 +61,7 @@ _SIGNATURES = {
     "mht_version": (C.c_int, []),
     "mht_last_error": (C.c_char_p, []),
     "mht_device_count": (C.c_int, []),
+    "mht_launch_count": (_i64, []),
     "mht_gate_batch_workspace": (_i64, [_i64, _i64]),
     "mht_gate_batch": (C.c_int, [C.POINTER(Model), _i64, _i64] + [_vp] * 13 + [_i64, _vp, _vp, _vp]),
     "mht_gate_batch_host": (C.c_int, [C.POINTER(Model), _i64, _i64] + [_vp] * 13 + [_i64, _vp]),

@@ -7,6 +7,7 @@
 namespace mht {
 
 static thread_local char g_err[512] = "";
+long long g_launches = 0;
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -44,3 +45,4 @@ int check_device() {
 extern "C" int mht_version(void) { return 100; }
 extern "C" const char *mht_last_error(void) { return mht::g_err; }
 extern "C" int mht_device_count(void) { return mht::probe_devices(); }
+extern "C" int64_t mht_launch_count(void) { return mht::g_launches; }

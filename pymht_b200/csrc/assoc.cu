@@ -35,7 +35,8 @@ namespace mht {
 constexpr double kFix = 17179869184.0;  // 2^34
 constexpr int kPatience = 10;
 constexpr double kShrink = 0.7;
-constexpr int kMaxCandPerTree = 192;
+constexpr int kMaxCandPerTree = 2048;   // per-tree candidate list limit (insertion sort, one thread)
+constexpr int kDomMax = 192;             // dominance reduction only for lists up to this length
 constexpr int kGreedyRounds = 40;
 constexpr int kGreedyEvery = 40;
 constexpr int kStallStop = 60;
@@ -88,6 +89,7 @@ __global__ void assoc_init_kernel(ColView c, AssocWork w, int *tstart, int *tend
             if (!warm) w.u[i] = 0.0;   // warm start: keep last scan's multipliers (rows persist W scans)
             w.best_u[i] = warm ? w.u[i] : 0.0;
             w.usage[i] = 0;
+            w.bbw.row_local[i] = -1;
         }
         if (i < 4) {
             w.stall_ctr[i] = 0;
@@ -459,11 +461,11 @@ __device__ __forceinline__ void du_apply_finish_body(ColView c, AssocWork w) {
 static void dual_update(const ColView &c, AssocWork &w, cudaStream_t s) {
     const int tb = (c.n_trees + 127) / 128;
     const int rb = tb > 64 ? tb : 64;
-    du_trees_kernel<<<tb, 128, 0, s>>>(c, w);
-    du_rows_kernel<<<rb, 256, 0, s>>>(c, w);
-    du_decide_kernel<<<tb, 128, 0, s>>>(c, w);
-    du_apply_kernel<<<rb, 256, 0, s>>>(c, w);
-    du_finish_kernel<<<tb, 128, 0, s>>>(c, w);
+    count_launch(), du_trees_kernel<<<tb, 128, 0, s>>>(c, w);
+    count_launch(), du_rows_kernel<<<rb, 256, 0, s>>>(c, w);
+    count_launch(), du_decide_kernel<<<tb, 128, 0, s>>>(c, w);
+    count_launch(), du_apply_kernel<<<rb, 256, 0, s>>>(c, w);
+    count_launch(), du_finish_kernel<<<tb, 128, 0, s>>>(c, w);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -869,9 +871,19 @@ __global__ void __launch_bounds__(1024, 1) final_bound_kernel(ColView c, AssocWo
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
         if (tstart[t] < 0) continue;
         const int cl = w.uf[t];
-        if (w.sel[t] < 0) {  // no primal solution reached this tree (greedy ran out of rounds)
-            w.sel[t] = w.targ[t];
-            atomicAdd(&w.info[11], 1);
+        if (w.sel[t] < 0) {
+            // no primal solution reached this tree (the greedy ran out of rounds): fall back to the tree's first
+            // column when it uses no row (forest columns: the all-miss leaf) -- always conflict free.  Only a tree
+            // without such a column keeps its Lagrangian choice, which may collide: flagged, never certified.
+            const int j0 = tstart[t];
+            bool row_free = true;
+            for (int k = 0; k < c.width; ++k) row_free = row_free && c.rows[(long long)k * c.stride + j0] < 0;
+            if (row_free) {
+                w.sel[t] = j0;
+            } else {
+                w.sel[t] = w.targ[t];
+                atomicAdd(&w.info[11], 1);
+            }
         }
         atomicAdd((unsigned long long *)&w.cl_m[cl], (unsigned long long)to_fix(key_f64(w.tmin[t])));
         atomicAdd((unsigned long long *)&w.cl_cost[cl], (unsigned long long)to_fix(col_cost(c, w.sel[t], t)));
@@ -1046,9 +1058,9 @@ __global__ void cand_dominance_kernel(ColView c, AssocWork w) {
     if (w.info[6]) return;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
         const int cnt = w.cand_cnt[t];
-        if (cnt < 2) continue;
+        if (cnt < 2 || cnt > kDomMax) continue;
         int *v = w.cand_col + w.cand_off[t];
-        unsigned long long drop[(kMaxCandPerTree + 63) / 64] = {0ull};
+        unsigned long long drop[(kDomMax + 63) / 64] = {0ull};
         for (int ib = 0; ib < cnt; ++ib) {
             const int b = v[ib];
             const double cb = col_cost(c, b, t);
@@ -1376,117 +1388,17 @@ __global__ void ls_round_end_kernel(AssocWork w) {
     w.ls_ctr[0] = 0;
 }
 
-// one thread per component: first-improvement local search on the incumbent over the candidate columns.
-//   1-opt: a tree switches to a cheaper candidate whose rows are free;
-//   2-opt: a tree takes a candidate that collides with exactly ONE other tree, which moves to its best
-//          candidate that is free afterwards, when the pair's total cost drops.
-// Tightens the upper bound before the exact search (the greedy primal is the weak side on big clusters).
-__global__ void __launch_bounds__(32) local_search_kernel(ColView c, AssocWork w, int max_sweeps) {
-    if (w.info[6]) return;
-    const int ncomp = w.info[4];
-    for (int comp = blockIdx.x; comp < ncomp; comp += gridDim.x) {
-        if (threadIdx.x != 0) continue;
-        const int off = w.comp_off[comp], k = w.comp_off[comp + 1] - off;
-        const int *trees = w.comp_trees + off;
-        for (int i = 0; i < k; ++i) {
-            const int t = trees[i], j = w.sel[t];
-            for (int kk = 0; kk < c.width; ++kk) {
-                const int r = c.rows[(long long)kk * c.stride + j];
-                if (r >= 0) w.row_holder[r] = t;
-            }
-        }
-        for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-            bool improved = false;
-            for (int i = 0; i < k; ++i) {
-                const int t = trees[i];
-                const int cur = w.sel[t];
-                const double cur_cost = col_cost(c, cur, t);
-                const int *v = w.cand_col + w.cand_off[t];
-                for (int q = 0; q < w.cand_cnt[t]; ++q) {
-                    const int j = v[q];
-                    if (j == cur) continue;
-                    const double dt = col_cost(c, j, t) - cur_cost;
-                    int other = -1, nother = 0;
-                    for (int kk = 0; kk < c.width && nother < 2; ++kk) {
-                        const int r = c.rows[(long long)kk * c.stride + j];
-                        if (r < 0) continue;
-                        const int h = w.row_holder[r];
-                        if (h >= 0 && h != t && h != other) {
-                            other = h;
-                            ++nother;
-                        }
-                    }
-                    int j2 = -1;
-                    double d2 = 0.0;
-                    if (nother == 0) {
-                        if (dt >= -1e-12) continue;
-                    } else if (nother == 1) {
-                        const int cur2 = w.sel[other];
-                        const double cur2_cost = col_cost(c, cur2, other);
-                        const int *v2 = w.cand_col + w.cand_off[other];
-                        double best2 = 1e300;
-                        for (int q2 = 0; q2 < w.cand_cnt[other]; ++q2) {
-                            const int cand2 = v2[q2];
-                            const double cc = col_cost(c, cand2, other);
-                            if (cc >= best2) continue;
-                            bool ok = true;
-                            for (int kk = 0; kk < c.width && ok; ++kk) {
-                                const int r2 = c.rows[(long long)kk * c.stride + cand2];
-                                if (r2 < 0) continue;
-                                for (int k3 = 0; k3 < c.width; ++k3)   // j takes its rows
-                                    if (c.rows[(long long)k3 * c.stride + j] == r2) ok = false;
-                                const int h = w.row_holder[r2];
-                                if (h >= 0 && h != other && h != t) ok = false;   // rows t holds now are released
-                            }
-                            if (ok) {
-                                best2 = cc;
-                                j2 = cand2;
-                            }
-                        }
-                        if (j2 < 0) continue;
-                        d2 = best2 - cur2_cost;
-                        if (dt + d2 >= -1e-12) continue;
-                    } else {
-                        continue;
-                    }
-                    // apply: release, then take
-                    for (int kk = 0; kk < c.width; ++kk) {
-                        const int r = c.rows[(long long)kk * c.stride + cur];
-                        if (r >= 0) w.row_holder[r] = -1;
-                    }
-                    if (j2 >= 0) {
-                        const int cur2 = w.sel[other];
-                        for (int kk = 0; kk < c.width; ++kk) {
-                            const int r = c.rows[(long long)kk * c.stride + cur2];
-                            if (r >= 0) w.row_holder[r] = -1;
-                        }
-                        for (int kk = 0; kk < c.width; ++kk) {
-                            const int r = c.rows[(long long)kk * c.stride + j2];
-                            if (r >= 0) w.row_holder[r] = other;
-                        }
-                        w.sel[other] = j2;
-                    }
-                    for (int kk = 0; kk < c.width; ++kk) {
-                        const int r = c.rows[(long long)kk * c.stride + j];
-                        if (r >= 0) w.row_holder[r] = t;
-                    }
-                    w.sel[t] = j;
-                    improved = true;
-                    break;   // re-evaluate this tree from its new incumbent on the next sweep
-                }
-            }
-            if (!improved) break;
-        }
-    }
-}
-
 // one CTA per component, thread 0 searches depth first with the Lagrangian bound
+// (components of up to kDfsMaxTrees trees: enumeration is cheap there; everything else, and whatever this search
+// gives up on, goes to the branch & bound below)
 __global__ void __launch_bounds__(32) branch_bound_kernel(ColView c, AssocWork w, int budget, double *fscratch) {
     if (w.info[6]) return;
     const int ncomp = w.info[4];
     for (int comp = blockIdx.x; comp < ncomp; comp += gridDim.x) {
         if (threadIdx.x != 0) continue;
         const int off = w.comp_off[comp], k = w.comp_off[comp + 1] - off;
+        w.bbw.comp_state[comp] = 0;
+        if (k > kDfsMaxTrees) continue;
         int *trees = w.comp_trees + off;
         // deterministic order: fewest candidates first, then tree index
         for (int i = 1; i < k; ++i) {
@@ -1519,9 +1431,7 @@ __global__ void __launch_bounds__(32) branch_bound_kernel(ColView c, AssocWork w
                 }
         }
         const double Lcomp = sum_m - sum_u;
-        // the single-thread search is only worth its latency on small components
-        const unsigned long long node_budget =
-            (unsigned long long)(k <= 64 ? budget : budget / 64);
+        const unsigned long long node_budget = (unsigned long long)budget;
         unsigned long long nodes = 0;
         int depth = 0;
         pos[0] = 0;
@@ -1581,8 +1491,375 @@ __global__ void __launch_bounds__(32) branch_bound_kernel(ColView c, AssocWork w
         }
         for (int i = 0; i < k; ++i) w.sel[trees[i]] = bestsel[i];
         atomicAdd(w.bb_nodes, nodes);
-        if (exhausted) atomicAdd(&w.info[5], 1);
+        if (!exhausted) w.bbw.comp_state[comp] = 1;
+        // the search marked the rows its candidates touch (bound bookkeeping): clear them for the next stage
+        for (int i = 0; i < k; ++i) {
+            const int t = trees[i];
+            const int *v = w.cand_col + w.cand_off[t];
+            for (int q = 0; q < w.cand_cnt[t]; ++q)
+                for (int kk = 0; kk < c.width; ++kk) {
+                    const int r = c.rows[(long long)kk * c.stride + v[q]];
+                    if (r >= 0) w.usage[r] = 0;
+                }
+        }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact repair of the open components: best-first Lagrangian branch & bound (bb_core.h), one CTA per
+// node evaluation, every CTA of the grid serving one shared node pool
+// ------------------------------------------------------------------------------------------------
+// single CTA: which components still need the search, offsets of their compacted cores
+__global__ void __launch_bounds__(1024, 1) bb_plan_kernel(ColView c, AssocWork w) {
+    BBWork &b = w.bbw;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 16; ++i) b.hdr[i] = 0;
+        b.p_ctr[0] = b.p_ctr[1] = b.p_ctr[2] = b.p_ctr[3] = 0;
+    }
+    __syncthreads();
+    if (w.info[6]) return;
+    const int ncomp = w.info[4];
+    __shared__ int n_open;
+    if (threadIdx.x == 0) n_open = 0;
+    __syncthreads();
+    // columns per component (cl_nrm is free here: reuse as scratch)
+    for (int k = threadIdx.x; k < ncomp; k += blockDim.x) {
+        int cols = 0;
+        for (int i = w.comp_off[k]; i < w.comp_off[k + 1]; ++i) cols += w.cand_cnt[w.comp_trees[i]];
+        w.cl_stall[k] = cols;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = 0, col_off = 0, tree_off = 0, max_c = 0, max_t = 0;
+        for (int k = 0; k < ncomp; ++k) {
+            if (b.comp_state[k]) continue;
+            const int nT = w.comp_off[k + 1] - w.comp_off[k], nC = w.cl_stall[k];
+            if (nC > b.max_cols || nT > b.max_trees || n >= kBBMaxNodes / 4) continue;   // stays open: uncertified
+            bb::Comp &p = b.comps[n];
+            p.nC = nC;
+            p.nT = nT;
+            p.nR = 0;
+            p.W = c.width;
+            p.row_stride = b.cap;
+            p.cost = b.c_cost + col_off;
+            p.tree = b.c_tree + col_off;
+            p.rows = b.c_rows + col_off;
+            p.tstart = b.t_start + tree_off + n;
+            p.nwords = (nC + 31) / 32;
+            p.ub_key = b.ub_key + n;
+            p.best_sel = b.best_sel + tree_off;
+            p.lock = b.lock + n;
+            b.lock[n] = 0;
+            b.row_cnt[n] = 0;
+            b.comp_unproven[n] = 0;
+            b.comp_nodes[n] = 0;
+            b.comp_slot[n] = k;
+            col_off += nC;
+            tree_off += nT;
+            max_c = max(max_c, nC);
+            max_t = max(max_t, nT);
+            ++n;
+        }
+        b.hdr[0] = n;
+        b.hdr[1] = max_c;
+        b.hdr[3] = max_t;
+        b.hdr[5] = col_off;
+    }
+}
+
+// one CTA per search component: compact its candidate columns, number its rows, cost of the incumbent
+__global__ void __launch_bounds__(256) bb_compact_kernel(ColView c, AssocWork w) {
+    BBWork &b = w.bbw;
+    const int n = b.hdr[0];
+    __shared__ double s_ub;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        bb::Comp &p = b.comps[i];
+        const int k = b.comp_slot[i];
+        const int *trees = w.comp_trees + w.comp_off[k];
+        int *tstart = (int *)p.tstart;
+        const long long col_off = p.cost - b.c_cost;
+        const long long tree_off = p.best_sel - b.best_sel;
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            double ub = 0.0;
+            for (int t = 0; t < p.nT; ++t) {
+                tstart[t] = acc;
+                acc += w.cand_cnt[trees[t]];
+                b.t_gtree[tree_off + t] = trees[t];
+                ub += col_cost(c, w.sel[trees[t]], trees[t]);
+            }
+            tstart[p.nT] = acc;
+            s_ub = ub;
+            b.ub_key[i] = bb::key_of(ub);
+        }
+        __syncthreads();
+        // columns: warp per tree, lanes over its candidates; rows marked for numbering
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int t = wid; t < p.nT; t += nw) {
+            const int gt = trees[t];
+            const int *v = w.cand_col + w.cand_off[gt];
+            const int cnt = w.cand_cnt[gt], base = tstart[t];
+            const int inc = w.sel[gt];
+            for (int q = lane; q < cnt; q += 32) {
+                const int j = v[q];
+                const long long lj = col_off + base + q;
+                b.c_cost[lj] = col_cost(c, j, gt);
+                b.c_tree[lj] = t;
+                b.c_gcol[lj] = j;
+                if (j == inc) p.best_sel[t] = base + q;
+                for (int kk = 0; kk < c.width; ++kk) {
+                    const int r = c.rows[(long long)kk * c.stride + j];
+                    if (r >= 0) b.row_local[r] = -2;
+                }
+            }
+        }
+        __syncthreads();
+        int *grow = b.r_grow + (long long)c.width * col_off;
+        for (int lj = threadIdx.x; lj < p.nC; lj += blockDim.x) {
+            const int j = b.c_gcol[col_off + lj];
+            for (int kk = 0; kk < c.width; ++kk) {
+                const int r = c.rows[(long long)kk * c.stride + j];
+                if (r >= 0 && atomicCAS(&b.row_local[r], -2, -3) == -2) grow[atomicAdd(&b.row_cnt[i], 1)] = r;
+            }
+        }
+        __syncthreads();
+        const int nR = b.row_cnt[i];
+        for (int q = threadIdx.x; q < nR; q += blockDim.x) b.row_local[grow[q]] = q;
+        __syncthreads();
+        for (int lj = threadIdx.x; lj < p.nC; lj += blockDim.x) {
+            const int j = b.c_gcol[col_off + lj];
+            for (int kk = 0; kk < c.width; ++kk) {
+                const int r = c.rows[(long long)kk * c.stride + j];
+                b.c_rows[(long long)kk * b.cap + col_off + lj] = r >= 0 ? b.row_local[r] : -1;
+            }
+        }
+        if (threadIdx.x == 0) {
+            p.nR = nR;
+            atomicMax(&b.hdr[2], nR);
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// pool geometry + one root node per component (all columns alive, the dual loop's multipliers)
+__global__ void __launch_bounds__(256) bb_root_kernel(ColView c, AssocWork w, double budget_ms) {
+    BBWork &b = w.bbw;
+    const int n = b.hdr[0];
+    if (n == 0) return;
+    const int node_words = (b.hdr[1] + 31) / 32, node_rows = max(b.hdr[2], 1);
+    const long long node_bytes = 4ll * node_words + 4ll * node_rows;
+    long long cap = b.pool_bytes / node_bytes;
+    if (cap > kBBMaxNodes) cap = kBBMaxNodes;
+    if (cap < 2ll * n + 8) {   // the pool cannot even hold the roots: the components stay open (uncertified)
+        if (blockIdx.x == 0 && threadIdx.x == 0) b.hdr[6] = 1;
+        return;
+    }
+    bb::Pool &pl = *b.pool;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        pl.cap = (int)cap;
+        pl.node_words = node_words;
+        pl.node_rows = node_rows;
+        pl.state = b.p_state;
+        pl.key = b.p_key;
+        pl.bound = b.p_bound;
+        pl.comp = b.p_comp;
+        pl.bt = b.p_bt;
+        pl.br = b.p_br;
+        pl.alive = (unsigned *)b.pool_mem;
+        pl.u = (float *)(b.pool_mem + 4ll * node_words * cap);
+        pl.outstanding = b.p_ctr;
+        pl.stop = b.p_ctr + 1;
+        pl.nodes = b.p_ctr + 2;
+        pl.iters = b.p_ctr + 3;
+        pl.comp_unproven = b.comp_unproven;
+        pl.comp_nodes = b.comp_nodes;
+        b.hdr[4] = (int)cap;
+        b.p_ctr[0] = n;
+        const unsigned long long now = global_timer_ns();
+        b.deadline[1] = now;
+        b.deadline[0] = now + (unsigned long long)(budget_ms * 1.0e6);
+    }
+    unsigned *alive = (unsigned *)b.pool_mem;
+    float *u = (float *)(b.pool_mem + 4ll * node_words * cap);
+    for (long long i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (long long)gridDim.x * blockDim.x)
+        b.p_state[i] = 0;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const bb::Comp &p = b.comps[i];
+        const long long col_off = p.cost - b.c_cost;
+        const int *grow = b.r_grow + (long long)c.width * col_off;
+        for (int wd = threadIdx.x; wd < p.nwords; wd += blockDim.x) {
+            const int left = p.nC - 32 * wd;
+            alive[(long long)i * node_words + wd] = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+        }
+        for (int r = threadIdx.x; r < p.nR; r += blockDim.x) u[(long long)i * node_rows + r] = (float)w.u[grow[r]];
+        if (threadIdx.x == 0) {
+            b.p_comp[i] = i;
+            b.p_bt[i] = -1;
+            b.p_br[i] = -1;
+            b.p_bound[i] = -1e300;
+            b.p_key[i] = -1e300;
+        }
+    }
+}
+// (separate launch: the root states become visible after every slot was cleared)
+__global__ void bb_open_roots_kernel(AssocWork w) {
+    BBWork &b = w.bbw;
+    if (b.hdr[6]) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) b.hdr[0] = 0;
+        return;
+    }
+    const int n = b.hdr[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) b.p_state[i] = 1;
+}
+
+struct DeviceCtx {
+    double *red_d;                 // [32] shared
+    long long *red_l;              // [32] shared
+    unsigned long long *word;      // [1] shared
+    unsigned char *smem;           // dynamic shared memory for the component state
+    size_t smem_bytes;
+    char *gscratch;                // this worker's global scratch
+    const BBWork *b;
+    __device__ int tid() const { return (int)threadIdx.x; }
+    __device__ int nthr() const { return (int)blockDim.x; }
+    __device__ void sync() { __syncthreads(); }
+    __device__ void amin64(unsigned long long *p, unsigned long long v) { atomicMin(p, v); }
+    __device__ void amax(int *p, int v) { atomicMax(p, v); }
+    __device__ void aadd(int *p, int v) { atomicAdd(p, v); }
+    __device__ int acas(int *p, int cmp, int val) { return atomicCAS(p, cmp, val); }
+    __device__ void fence() { __threadfence(); }
+    __device__ void backoff() { __nanosleep(2000); }
+    __device__ bool expired() { return global_timer_ns() > b->deadline[0]; }
+    // deterministic block sums: warp shuffles, then every thread adds the warp partials in warp order
+    __device__ double sum(double v) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red_d[threadIdx.x >> 5] = v;
+        __syncthreads();
+        double s = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red_d[i];
+        __syncthreads();
+        return s;
+    }
+    __device__ long long maxll(long long v) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const long long x = __shfl_xor_sync(0xffffffffu, v, o);
+            v = x > v ? x : v;
+        }
+        if ((threadIdx.x & 31) == 0) red_l[threadIdx.x >> 5] = v;
+        __syncthreads();
+        long long s = red_l[0];
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) s = red_l[i] > s ? red_l[i] : s;
+        __syncthreads();
+        return s;
+    }
+    __device__ unsigned long long bcast(unsigned long long v) {
+        if (threadIdx.x == 0) *word = v;
+        __syncthreads();
+        const unsigned long long r = *word;
+        __syncthreads();
+        return r;
+    }
+    // component state in shared memory when it fits, else in this worker's global scratch
+    __device__ bool bind(const bb::Comp &p, bb::Scratch &s) {
+        if (p.nC > b->max_cols || p.nR > b->max_rows || p.nT > b->max_trees) return false;
+        char *g = gscratch;
+        auto take = [&](size_t bytes) { char *r = g; g += (bytes + 15) / 16 * 16; return r; };
+        s.rc = (double *)take(8ull * b->max_cols);
+        s.freq = (int *)take(4ull * b->max_cols);
+        s.ubest = (double *)take(8ull * b->max_rows);
+        s.best_targ = (int *)take(4ull * b->max_trees);
+        s.cand_d = (double *)take(8ull * b->max_trees);
+        s.cand_r = (int *)take(4ull * b->max_trees);
+        const size_t need = (8ull * p.nR + 15) / 16 * 16 + (4ull * p.nR + 15) / 16 * 16 + (8ull * p.nT + 15) / 16 * 16 +
+                            (4ull * p.nT + 15) / 16 * 16 + (4ull * p.nwords + 15) / 16 * 16;
+        if (need <= smem_bytes) {
+            unsigned char *q = smem;
+            auto stake = [&](size_t bytes) { unsigned char *r = q; q += (bytes + 15) / 16 * 16; return r; };
+            s.u = (double *)stake(8ull * p.nR);
+            s.tmin = (unsigned long long *)stake(8ull * p.nT);
+            s.usage = (int *)stake(4ull * p.nR);
+            s.targ = (int *)stake(4ull * p.nT);
+            s.alive = (unsigned *)stake(4ull * p.nwords);
+        } else {
+            s.u = (double *)take(8ull * b->max_rows);
+            s.tmin = (unsigned long long *)take(8ull * b->max_trees);
+            s.usage = (int *)take(4ull * b->max_rows);
+            s.targ = (int *)take(4ull * b->max_trees);
+            s.alive = (unsigned *)take(4ull * ((b->max_cols + 31) / 32));
+        }
+        return true;
+    }
+};
+
+__host__ __device__ inline long long bb_scratch_bytes(long long max_cols, long long max_rows, long long max_trees) {
+    auto al16 = [](long long v) { return (v + 15) / 16 * 16; };
+    return al16(8 * max_cols) + al16(4 * max_cols) + al16(8 * max_rows) + al16(4 * max_trees) + al16(8 * max_trees) +
+           al16(4 * max_trees) + al16(8 * max_rows) + al16(8 * max_trees) + al16(4 * max_rows) + al16(4 * max_trees) +
+           al16(4 * ((max_cols + 31) / 32)) + 256;
+}
+
+__global__ void __launch_bounds__(kBBThreads, 1) bb_search_kernel(AssocWork w, int K_root, int K_node, int max_nodes) {
+    extern __shared__ __align__(16) unsigned char bb_smem[];
+    __shared__ double red_d[32];
+    __shared__ long long red_l[32];
+    __shared__ unsigned long long word;
+    const BBWork &b = w.bbw;
+    if (b.hdr[0] == 0) return;
+    DeviceCtx ctx;
+    ctx.red_d = red_d;
+    ctx.red_l = red_l;
+    ctx.word = &word;
+    ctx.smem = bb_smem;
+    unsigned dyn;
+    asm volatile("mov.u32 %0, %dynamic_smem_size;" : "=r"(dyn));
+    ctx.smem_bytes = dyn;
+    ctx.gscratch = b.scratch_mem + (long long)blockIdx.x * b.scratch_per_worker;
+    ctx.b = &b;
+    bb::Scratch s;
+    bb::Pool pl = *b.pool;
+    bb::worker(ctx, b.comps, pl, s, K_root, K_node, max_nodes);
+}
+
+// results of the search: selection of every searched component, proven flags
+__global__ void __launch_bounds__(256) bb_writeback_kernel(ColView c, AssocWork w) {
+    BBWork &b = w.bbw;
+    const int n = b.hdr[0];
+    if (n == 0) return;
+    // nodes still in the pool belong to unfinished components
+    const int cap = b.hdr[4];
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < cap; i += blockDim.x)
+            if (b.p_state[i] != 0) b.comp_unproven[b.p_comp[i]] = 1;
+        if (threadIdx.x == 0) {
+            atomicAdd(w.bb_nodes, (unsigned long long)b.p_ctr[2]);
+            w.info[14] = b.p_ctr[3];   // subgradient iterations spent inside the search
+        }
+    }
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const bb::Comp &p = b.comps[i];
+        const long long col_off = p.cost - b.c_cost;
+        const long long tree_off = p.best_sel - b.best_sel;
+        for (int t = threadIdx.x; t < p.nT; t += blockDim.x)
+            w.sel[b.t_gtree[tree_off + t]] = b.c_gcol[col_off + p.best_sel[t]];
+        // rows of this component leave the numbering table clean for the next solve
+        const int *grow = b.r_grow + (long long)c.width * col_off;
+        for (int r = threadIdx.x; r < p.nR; r += blockDim.x) b.row_local[grow[r]] = -1;
+    }
+}
+// (after the grid finished marking unproven components)
+__global__ void bb_state_kernel(AssocWork w) {
+    BBWork &b = w.bbw;
+    const int n = b.hdr[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (!b.comp_unproven[i]) b.comp_state[b.comp_slot[i]] = 1;
 }
 
 // single CTA: final objective and certificate
@@ -1597,7 +1874,11 @@ __global__ void __launch_bounds__(1024, 1) final_objective_kernel(ColView c, Ass
     if (threadIdx.x == 0) {
         w.objective[1] = from_fix(ob);
         w.info[12] = w.act_n[0];
-        w.info[10] = (w.info[5] == 0 && w.info[6] == 0 && w.info[11] == 0) ? 1 : 0;  // certified
+        int open = 0;
+        if (!w.info[6])
+            for (int k = 0; k < w.info[4]; ++k) open += w.bbw.comp_state[k] ? 0 : 1;
+        w.info[5] = open;   // components whose exact search did not finish
+        w.info[10] = (open == 0 && w.info[6] == 0 && w.info[11] == 0) ? 1 : 0;  // certified
     }
 }
 
@@ -1679,6 +1960,49 @@ static int64_t carve_all(Carver &cv, int64_t cap_cols, int64_t T, int64_t R, int
     d.objective = cv.take<double>(2);
     int *ts = cv.take<int>(T), *te = cv.take<int>(T);
     double *fs = cv.take<double>(4 * T + 8);
+    {   // exact repair (bb_core.h)
+        BBWork &b = d.bbw;
+        const int64_t cap = cap_cand;
+        b.cap = cap;
+        b.comps = cv.take<bb::Comp>(T);
+        b.comp_state = cv.take<int>(T);
+        b.comp_slot = cv.take<int>(T);
+        b.hdr = cv.take<int>(16);
+        b.deadline = cv.take<unsigned long long>(2);
+        b.c_cost = cv.take<double>(cap);
+        b.c_tree = cv.take<int>(cap);
+        b.c_gcol = cv.take<int>(cap);
+        b.c_rows = cv.take<int>(cap * MHT_MAX_WINDOW);
+        b.r_grow = cv.take<int>(cap * MHT_MAX_WINDOW);
+        b.t_start = cv.take<int>(2 * T + 2);
+        b.t_gtree = cv.take<int>(T);
+        b.best_sel = cv.take<int>(T);
+        b.ub_key = cv.take<unsigned long long>(T);
+        b.lock = cv.take<int>(T);
+        b.row_local = cv.take<int>(R);
+        b.row_cnt = cv.take<int>(T);
+        b.comp_unproven = cv.take<int>(T);
+        b.comp_nodes = cv.take<int>(T);
+        b.pool = cv.take<bb::Pool>(1);
+        b.p_state = cv.take<int>(kBBMaxNodes);
+        b.p_comp = cv.take<int>(kBBMaxNodes);
+        b.p_bt = cv.take<int>(kBBMaxNodes);
+        b.p_br = cv.take<int>(kBBMaxNodes);
+        b.p_key = cv.take<double>(kBBMaxNodes);
+        b.p_bound = cv.take<double>(kBBMaxNodes);
+        b.p_ctr = cv.take<int>(8);
+        b.max_cols = (int)(cap < kBBMaxCols ? cap : kBBMaxCols);
+        const int64_t rows_bound = (int64_t)b.max_cols * MHT_MAX_WINDOW;
+        b.max_rows = (int)(R < rows_bound ? R : rows_bound);
+        b.max_trees = (int)T;
+        b.scratch_per_worker = bb_scratch_bytes(b.max_cols, b.max_rows, b.max_trees);
+        b.scratch_mem = cv.take<char>(b.scratch_per_worker * kBBWorkers);
+        int64_t pool = cap * 2048;
+        if (pool < (16ll << 20)) pool = 16ll << 20;
+        if (pool > (1ll << 30)) pool = 1ll << 30;
+        b.pool_bytes = pool;
+        b.pool_mem = cv.take<char>(pool);
+    }
     d.tstart = ts;
     if (w) *w = d;
     if (tstart) *tstart = ts;
@@ -1704,7 +2028,7 @@ int assoc_begin(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s, bo
     (void)grid_dim;
     int n = (c.n_trees + 1 > c.n_rows ? c.n_trees + 1 : c.n_rows);
     if (n < kAssocInfo) n = kAssocInfo;  // the status words are cleared by the same kernel
-    assoc_init_kernel<<<(n + 255) / 256, 256, 0, s>>>(c, w, w.tstart, g_tend, warm ? 1 : 0);
+    count_launch(), assoc_init_kernel<<<(n + 255) / 256, 256, 0, s>>>(c, w, w.tstart, g_tend, warm ? 1 : 0);
     MHT_CUDA(cudaGetLastError());
     return MHT_OK;
 }
@@ -1714,12 +2038,12 @@ static int cluster_phase(const ColView &c, AssocWork &w, int grid_dim, cudaStrea
     const int T = c.n_trees;
     if (!pre_unioned)
         if (int rc = assoc_begin(c, w, grid_dim, s, warm)) return rc;
-    assoc_init_cols_kernel<<<grid_dim, 256, 0, s>>>(c, w, g_tstart, g_tend);
-    if (!pre_unioned) uf_union_cols_kernel<<<grid_dim, 256, 0, s>>>(c, w.uf, w.row_owner, w.row_mark);
-    if (warm) warm_fix_kernel<<<(c.n_rows + 255) / 256, 256, 0, s>>>(c.n_rows, w.row_mark, w.u, w.best_u);
-    uf_flatten_kernel<<<(T + 255) / 256, 256, 0, s>>>(T, w.uf);
-    row_list_kernel<<<(c.n_rows + 255) / 256, 256, 0, s>>>(c.n_rows, w.row_owner, w.row_list, w.row_n);
-    cluster_stats_kernel<<<1, 1024, 0, s>>>(T, w.uf, g_tstart, w.cl_nrm, w.info);
+    count_launch(), assoc_init_cols_kernel<<<grid_dim, 256, 0, s>>>(c, w, g_tstart, g_tend);
+    if (!pre_unioned) count_launch(), uf_union_cols_kernel<<<grid_dim, 256, 0, s>>>(c, w.uf, w.row_owner, w.row_mark);
+    if (warm) count_launch(), warm_fix_kernel<<<(c.n_rows + 255) / 256, 256, 0, s>>>(c.n_rows, w.row_mark, w.u, w.best_u);
+    count_launch(), uf_flatten_kernel<<<(T + 255) / 256, 256, 0, s>>>(T, w.uf);
+    count_launch(), row_list_kernel<<<(c.n_rows + 255) / 256, 256, 0, s>>>(c.n_rows, w.row_owner, w.row_list, w.row_n);
+    count_launch(), cluster_stats_kernel<<<1, 1024, 0, s>>>(T, w.uf, g_tstart, w.cl_nrm, w.info);
     MHT_CUDA(cudaGetLastError());
     return MHT_OK;
 }
@@ -1729,13 +2053,13 @@ int assoc_cluster(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s) 
 }
 
 static void greedy_pass(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s) {
-    greedy_init_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
+    count_launch(), greedy_init_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
     for (int r = 0; r < kGreedyRounds; ++r) {
-        greedy_prop_kernel<<<grid_dim, 256, 0, s>>>(c, w);
-        greedy_arg_kernel<<<grid_dim, 256, 0, s>>>(c, w);
-        greedy_commit_kernel<<<1, 1024, 0, s>>>(c, w);
+        count_launch(), greedy_prop_kernel<<<grid_dim, 256, 0, s>>>(c, w);
+        count_launch(), greedy_arg_kernel<<<grid_dim, 256, 0, s>>>(c, w);
+        count_launch(), greedy_commit_kernel<<<1, 1024, 0, s>>>(c, w);
     }
-    greedy_finish_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
+    count_launch(), greedy_finish_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
 }
 
 static int persistent_grid() {
@@ -1758,23 +2082,49 @@ static int dual_loop(const ColView &c, AssocWork &w, int iters, int grid_dim, cu
     void *args[] = {&cc, &ww, &iters, &greedy_every};
     // grid.sync cost grows with the grid: the active list (~1e5 columns) gets one CTA per SM
     const int grid = grid_dim < persistent_grid() ? grid_dim : persistent_grid();
+    count_launch();
     MHT_CUDA(cudaLaunchCooperativeKernel((void *)dual_loop_persistent_kernel, dim3(grid), dim3(256), args,
                                          0, s));
     return MHT_OK;
 }
 
+// incidences (rows >= 0) of the columns the dual loop iterates on -> info[15]
+__global__ void __launch_bounds__(256) nnz_kernel(ColView c, AssocWork w) {
+    const int n = *c.n_ptr;
+    int cnt = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int j = c.idx ? c.idx[i] : i;
+        for (int k = 0; k < c.width; ++k) cnt += c.rows[(long long)k * c.stride + j] >= 0 ? 1 : 0;
+    }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&w.info[15], cnt);
+}
+
 int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, int grid_dim, cudaStream_t s,
-                cudaEvent_t after_cluster, bool warm_start, bool sift, bool pre_unioned) {
+                AssocEvents *ev, bool warm_start, bool sift, bool pre_unioned, double exact_ms,
+                int exact_nodes) {
     if (int rc = cluster_phase(c, w, grid_dim, s, warm_start, pre_unioned)) return rc;
-    if (after_cluster) MHT_CUDA(cudaEventRecord(after_cluster, s));
+    if (ev && ev->after_cluster) MHT_CUDA(cudaEventRecord(ev->after_cluster, s));
+    if (ev) ev->n_dual = 0;
+    auto timed_loop = [&](const ColView &v, int iters, int g) -> int {
+        const bool rec = ev && ev->n_dual < 4 && ev->dual[2 * ev->n_dual];
+        if (rec) MHT_CUDA(cudaEventRecord(ev->dual[2 * ev->n_dual], s));
+        if (int rc = dual_loop(v, w, iters, g, s)) return rc;
+        if (rec) {
+            MHT_CUDA(cudaEventRecord(ev->dual[2 * ev->n_dual + 1], s));
+            ev->n_dual += 1;
+        }
+        return MHT_OK;
+    };
     // iteration 0 settles every conflict-free cluster (all singletons) exactly
-    dual_rc_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
-    dual_arg_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
+    count_launch(), dual_rc_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
+    count_launch(), dual_arg_kernel<false><<<grid_dim, 256, 0, s>>>(c, w);
     dual_update(c, w, s);
     if (!sift) {
         // small problem: iterations cost ~25 us each, so give the bound 4x the budget (the loop leaves as soon
         // as every cluster is settled or nothing has moved for kStallStop iterations)
-        if (int rc = dual_loop(c, w, 4 * max_iters, grid_dim, s)) return rc;
+        count_launch(), nnz_kernel<<<grid_dim, 256, 0, s>>>(c, w);
+        if (int rc = timed_loop(c, 4 * max_iters, grid_dim)) return rc;
     } else {
         // sifting: price all columns, iterate on the active list, re-price; kSiftRounds times
         ColView a = c;
@@ -1784,57 +2134,82 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
         const int act_grid = act_grid_env;
         static const int sift_rounds = getenv("MHT_SIFT_ROUNDS") ? atoi(getenv("MHT_SIFT_ROUNDS")) : kSiftRounds;
         for (int round = 0; round < sift_rounds; ++round) {
-            if (round) sift_rearm_kernel<<<1, 1024, 0, s>>>(c, w);
-            dual_rc_kernel<true><<<grid_dim, 256, 0, s>>>(c, w);
-            active_count_kernel<<<grid_dim, 256, 0, s>>>(c, w);
-            active_scan_kernel<<<1, 1024, 0, s>>>(c, w);
-            active_scatter_kernel<<<grid_dim, 256, 0, s>>>(c, w);
-            reset_tree_min_kernel<<<(c.n_trees + 255) / 256, 256, 0, s>>>(c.n_trees, w);
-            if (int rc = dual_loop(a, w, max_iters, act_grid, s)) return rc;
+            if (round) count_launch(), sift_rearm_kernel<<<1, 1024, 0, s>>>(c, w);
+            count_launch(), dual_rc_kernel<true><<<grid_dim, 256, 0, s>>>(c, w);
+            count_launch(), active_count_kernel<<<grid_dim, 256, 0, s>>>(c, w);
+            count_launch(), active_scan_kernel<<<1, 1024, 0, s>>>(c, w);
+            count_launch(), active_scatter_kernel<<<grid_dim, 256, 0, s>>>(c, w);
+            count_launch(), reset_tree_min_kernel<<<(c.n_trees + 255) / 256, 256, 0, s>>>(c.n_trees, w);
+            if (round == sift_rounds - 1) count_launch(), nnz_kernel<<<act_grid, 256, 0, s>>>(a, w);
+            if (int rc = timed_loop(a, max_iters, act_grid)) return rc;
         }
     }
     MHT_CUDA(cudaGetLastError());
     // final multipliers -> reduced costs, bound, candidates, exact repair
-    final_prepare_kernel<<<1, 1024, 0, s>>>(c, w);
-    dual_rc_kernel<true><<<grid_dim, 256, 0, s>>>(c, w);
-    dual_arg_kernel<true><<<grid_dim, 256, 0, s>>>(c, w);
+    count_launch(), final_prepare_kernel<<<1, 1024, 0, s>>>(c, w);
+    count_launch(), dual_rc_kernel<true><<<grid_dim, 256, 0, s>>>(c, w);
+    count_launch(), dual_arg_kernel<true><<<grid_dim, 256, 0, s>>>(c, w);
     {   // parallel local search on the incumbent (see ls_propose_kernel)
         static const int ls_rounds = getenv("MHT_LS_ROUNDS") ? atoi(getenv("MHT_LS_ROUNDS")) : 10;
         const int tb = (c.n_trees + 127) / 128, wb = (c.n_trees + 7) / 8;
         if (ls_rounds > 0) {
             MHT_CUDA(cudaMemsetAsync(w.ls_ctr, 0, 4 * sizeof(int), s));
             MHT_CUDA(cudaMemsetAsync(w.row_bid, 0xff, sizeof(unsigned long long) * (size_t)c.n_rows, s));
-            ls_begin_kernel<<<tb, 128, 0, s>>>(c, w, g_tstart);
-            ls_shortlist_kernel<<<c.n_trees < 8 * kSMs ? c.n_trees : 8 * kSMs, 256, 0, s>>>(c, w, g_tstart, g_tend);
+            count_launch(), ls_begin_kernel<<<tb, 128, 0, s>>>(c, w, g_tstart);
+            count_launch(), ls_shortlist_kernel<<<c.n_trees < 8 * kSMs ? c.n_trees : 8 * kSMs, 256, 0, s>>>(c, w, g_tstart, g_tend);
             for (int round = 0; round < ls_rounds; ++round) {
-                ls_propose_kernel<<<wb, 256, 0, s>>>(c, w, g_tstart);
-                ls_apply_kernel<<<tb, 128, 0, s>>>(c, w);
-                ls_clear_kernel<<<tb, 128, 0, s>>>(c, w);
-                ls_round_end_kernel<<<1, 1, 0, s>>>(w);
+                count_launch(), ls_propose_kernel<<<wb, 256, 0, s>>>(c, w, g_tstart);
+                count_launch(), ls_apply_kernel<<<tb, 128, 0, s>>>(c, w);
+                count_launch(), ls_clear_kernel<<<tb, 128, 0, s>>>(c, w);
+                count_launch(), ls_round_end_kernel<<<1, 1, 0, s>>>(w);
             }
             // the candidate-based search below keeps its own holder table
             MHT_CUDA(cudaMemsetAsync(w.row_holder, 0xff, sizeof(int) * (size_t)c.n_rows, s));
         }
     }
-    final_bound_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
-    cand_count_kernel<<<grid_dim, 256, 0, s>>>(c, w);
-    cand_scan_kernel<<<1, 1024, 0, s>>>(c, w);
-    cand_fill_kernel<<<grid_dim, 256, 0, s>>>(c, w);
+    count_launch(), final_bound_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
+    count_launch(), cand_count_kernel<<<grid_dim, 256, 0, s>>>(c, w);
+    count_launch(), cand_scan_kernel<<<1, 1024, 0, s>>>(c, w);
+    count_launch(), cand_fill_kernel<<<grid_dim, 256, 0, s>>>(c, w);
     {
         const int tb = (c.n_trees + 127) / 128, rb = (c.n_rows + 255) / 256 < 1024 ? (c.n_rows + 255) / 256 : 1024;
-        cand_sort_kernel<<<tb, 128, 0, s>>>(c, w);
+        count_launch(), cand_sort_kernel<<<tb, 128, 0, s>>>(c, w);
         for (int round = 0; round < 3; ++round) {
-            contest_reset_kernel<<<rb, 256, 0, s>>>(w);
-            contest_mark_kernel<<<tb, 128, 0, s>>>(c, w, nullptr);
-            cand_dominance_kernel<<<tb, 128, 0, s>>>(c, w);
+            count_launch(), contest_reset_kernel<<<rb, 256, 0, s>>>(w);
+            count_launch(), contest_mark_kernel<<<tb, 128, 0, s>>>(c, w, nullptr);
+            count_launch(), cand_dominance_kernel<<<tb, 128, 0, s>>>(c, w);
         }
-        contest_reset_kernel<<<rb, 256, 0, s>>>(w);
-        contest_mark_kernel<<<tb, 128, 0, s>>>(c, w, w.comp_uf);
+        count_launch(), contest_reset_kernel<<<rb, 256, 0, s>>>(w);
+        count_launch(), contest_mark_kernel<<<tb, 128, 0, s>>>(c, w, w.comp_uf);
     }
-    comp_build_kernel<<<1, 1024, 0, s>>>(c, w);
-    local_search_kernel<<<kSMs * 4, 32, 0, s>>>(c, w, 50);
-    branch_bound_kernel<<<kSMs * 4, 32, 0, s>>>(c, w, bb_budget, g_fscratch);
-    final_objective_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
+    count_launch(), comp_build_kernel<<<1, 1024, 0, s>>>(c, w);
+    count_launch(), branch_bound_kernel<<<kSMs * 4, 32, 0, s>>>(c, w, bb_budget, g_fscratch);
+    {   // exact repair of what is still open (bb_core.h)
+        static const int k_root = getenv("MHT_BB_KROOT") ? atoi(getenv("MHT_BB_KROOT")) : 200;
+        static const int k_node = getenv("MHT_BB_KNODE") ? atoi(getenv("MHT_BB_KNODE")) : 60;
+        static const double env_ms = getenv("MHT_BB_MS") ? atof(getenv("MHT_BB_MS")) : -1.0;
+        const double ms = env_ms >= 0.0 ? env_ms : exact_ms;
+        count_launch(), bb_plan_kernel<<<1, 1024, 0, s>>>(c, w);
+        if (ms > 0.0) {
+            count_launch(), bb_compact_kernel<<<kSMs, 256, 0, s>>>(c, w);
+            count_launch(), bb_root_kernel<<<kSMs, 256, 0, s>>>(c, w, ms);
+            count_launch(), bb_open_roots_kernel<<<4, 256, 0, s>>>(w);
+            static int smem_bytes = 0;
+            if (!smem_bytes) {
+                int dev = 0, optin = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+                smem_bytes = optin - 4096;   // static shared memory of the kernel + reserve
+                if (smem_bytes < 32768) smem_bytes = 32768;
+                MHT_CUDA(cudaFuncSetAttribute(bb_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            }
+            count_launch(), bb_search_kernel<<<kBBWorkers, kBBThreads, smem_bytes, s>>>(w, k_root, k_node, exact_nodes);
+            count_launch(), bb_writeback_kernel<<<kSMs, 256, 0, s>>>(c, w);
+            count_launch(), bb_state_kernel<<<4, 256, 0, s>>>(w);
+        }
+        if (ev && ev->exact_end) MHT_CUDA(cudaEventRecord(ev->exact_end, s));
+    }
+    count_launch(), final_objective_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
     MHT_CUDA(cudaGetLastError());
     return MHT_OK;
 }
@@ -1898,7 +2273,7 @@ extern "C" int mht_assoc_solve(int64_t n_cols, int64_t n_trees, int64_t n_rows, 
     AssocWork w;
     if (int rc = make_view(n_cols, n_trees, n_rows, width, d_col_cost, d_col_tree, d_col_rows, d_work, &c, &w, s))
         return rc;
-    if (int rc = assoc_solve(c, w, 200, 2000000, kSMs * 4, s, nullptr, false, n_cols > 2000000)) return rc;
+    if (int rc = assoc_solve(c, w, 200, 4096, kSMs * 4, s, nullptr, false, n_cols > 2000000, false, 10000.0)) return rc;
     MHT_CUDA(cudaMemcpyAsync(d_selected_col, w.sel, n_trees * sizeof(int), cudaMemcpyDeviceToDevice, s));
     int info[kAssocInfo];
     double obj[2];

@@ -2,6 +2,7 @@
 // operators and the forest.  See assoc.cu for the algorithm.
 #pragma once
 #include "common.cuh"
+#include "bb_core.h"
 
 namespace mht {
 
@@ -23,6 +24,43 @@ struct ColView {
     int width;
     int n_trees;
     int n_rows;
+};
+
+// Exact repair (bb_core.h): compacted cores of the open components, node pool, worker scratch.
+constexpr int kBBMaxNodes = 1 << 16;     // node slots (the pool memory may allow fewer)
+constexpr int kBBMaxCols = 1 << 18;      // columns of one component the search accepts
+constexpr int kBBWorkers = kSMs;         // one CTA per SM
+constexpr int kBBThreads = 512;
+constexpr int kDfsMaxTrees = 16;         // components up to this size go to the depth-first enumeration first
+
+struct BBWork {
+    bb::Comp *comps;            // [T]
+    int *comp_state;            // [T] per component slot: 1 = solved exactly
+    int *comp_slot;             // [T] search component -> component slot
+    int *hdr;                   // [16]: 0 n search comps, 1 max nC, 2 max nR, 3 max nT, 4 pool cap, 5 total cols
+    unsigned long long *deadline;   // [2] globaltimer deadline (ns), start
+    double *c_cost;             // [cap]
+    int *c_tree, *c_gcol;       // [cap]
+    int *c_rows;                // [W][cap]
+    int *r_grow;                // [W * cap] global row of each local row, per component at W * col_off
+    int *t_start;               // [2T + 2]
+    int *t_gtree;               // [T]
+    int *best_sel;              // [T]
+    unsigned long long *ub_key; // [T]
+    int *lock;                  // [T]
+    int *row_local;             // [R] global row -> local row of its component
+    int *row_cnt;               // [T]
+    int *comp_unproven, *comp_nodes;   // [T]
+    bb::Pool *pool;             // device copy of the pool descriptor
+    int *p_state, *p_comp, *p_bt, *p_br;   // [kBBMaxNodes]
+    double *p_key, *p_bound;    // [kBBMaxNodes]
+    int *p_ctr;                 // [8]: outstanding, stop, nodes, iters
+    char *pool_mem;
+    long long pool_bytes;
+    char *scratch_mem;
+    long long scratch_per_worker;
+    long long cap;              // = cap_cand
+    int max_cols, max_rows, max_trees;   // dimensions the worker scratch is sized for
 };
 
 struct AssocWork {
@@ -73,9 +111,12 @@ struct AssocWork {
     long long cap_cand;
     // device status words
     int *info;                 // [kAssocInfo]: 0 all_done, 1 iters, 2 greedy_left, 3 n_cand, 4 n_comp,
-                               // 5 uncertified, 6 cand_overflow, 7 n_clusters, 8 n_multi, 9 max_comp
+                               // 5 open components, 6 cand_overflow, 7 n_clusters, 8 n_multi, 9 max_comp, 10 certified,
+                               // 11 trees without feasible incumbent, 12 n_active, 13 candidates before dominance,
+                               // 14 iterations inside the exact search, 15 nnz of the columns the dual loop iterates on
     unsigned long long *bb_nodes;
     double *objective;         // [2]: lower bound, objective
+    BBWork bbw;
 };
 
 // ---- lock-free union-find shared with the forest's emit kernel (label = smallest tree index) ----
@@ -125,8 +166,16 @@ int assoc_begin(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s, bo
 // cluster labels only (uf[t] = smallest tree index of the component); async
 int assoc_cluster(const ColView &c, AssocWork &w, int grid_dim, cudaStream_t s);
 // full solve; async; results in w.sel / w.info / w.objective
+// optional CUDA events for the stage timers of mht_scan_info
+struct AssocEvents {
+    cudaEvent_t after_cluster = nullptr;
+    cudaEvent_t dual[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // begin/end per loop launch
+    int n_dual = 0;                       // out: event pairs recorded
+    cudaEvent_t exact_begin = nullptr, exact_end = nullptr;
+};
+// exact_ms / exact_nodes: wall-clock and node budget of the exact repair (branch & bound) of this solve
 int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, int grid_dim, cudaStream_t s,
-                cudaEvent_t after_cluster = nullptr, bool warm_start = false, bool sift = false,
-                bool pre_unioned = false);
+                AssocEvents *ev = nullptr, bool warm_start = false, bool sift = false,
+                bool pre_unioned = false, double exact_ms = 50.0, int exact_nodes = 1 << 30);
 
 }  // namespace mht

@@ -12,6 +12,8 @@
 namespace mht {
 
 void set_error(const char *fmt, ...);
+extern long long g_launches;   // kernels launched by this library (mht_launch_count)
+static inline void count_launch() { ++g_launches; }
 int check_device();  // MHT_OK or MHT_E_NODEVICE
 
 #define MHT_CUDA(expr)                                                                         \

@@ -65,6 +65,7 @@ struct ScanStatus {  // device status word copied back every scan
     int assoc[kAssocInfo];
     unsigned long long bb_nodes;
     double lower_bound, objective;
+    int rows_active, pad;
 };
 
 struct TrunkNode {
@@ -112,6 +113,8 @@ struct mht_forest {
     std::vector<std::vector<double>> dead_hist;   // per slot: window records (leaf -> root) kept for dead tracks
     cudaStream_t stream;
     cudaEvent_t ev[6];
+    cudaEvent_t evx[10];       // dual-loop launches (4 pairs) + exact repair begin/end
+    int n_dual_ev = 0;
     // host mirrors
     std::vector<int> h_alive, h_root_scan, h_init_scan, h_last_pos;
     std::vector<std::vector<TrunkNode>> trunk;
@@ -742,6 +745,7 @@ struct UpdateArgs {
     const int *assoc_info;
     const unsigned long long *bb_nodes;
     const double *objective;
+    const int *row_n;
     mht_model model;
     double score_upper, cnllr_upper, radar_range, px, py;
 };
@@ -763,6 +767,7 @@ __global__ void track_update_kernel(UpdateArgs a) {
     if (t == 0) {
         for (int i = 0; i < kAssocInfo; ++i) a.status->assoc[i] = a.assoc_info[i];
         a.status->bb_nodes = *a.bb_nodes;
+        a.status->rows_active = *a.row_n;
         a.status->lower_bound = a.objective[0];
         a.status->objective = a.objective[1];
     }
@@ -1013,6 +1018,7 @@ static void fill_update_args(mht_forest *f, UpdateArgs *u) {
     u->assoc_info = f->aw.info;
     u->bb_nodes = f->aw.bb_nodes;
     u->objective = f->aw.objective;
+    u->row_n = f->aw.row_n;
     u->model = f->cfg.model;
     u->score_upper = f->cfg.score_upper;
     u->cnllr_upper = f->cfg.cnllr_upper;
@@ -1122,16 +1128,16 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
         if (int rc = assoc_begin(c, f->aw, grid_dim, s, k > 1)) return rc;
         MHT_CUDA(cudaMemsetAsync(f->used_d, 0, (size_t)(M ? M : 1), s));
         MHT_CUDA(cudaMemsetAsync(f->tm_bits, 0, sizeof(unsigned) * (size_t)f->T * f->tm_words, s));
-        live_scan_kernel<<<1, 1024, 0, s>>>(a);
-        pat_table_kernel<<<f->T, 128, 0, s>>>(a);
+        count_launch(), live_scan_kernel<<<1, 1024, 0, s>>>(a);
+        count_launch(), pat_table_kernel<<<f->T, 128, 0, s>>>(a);
         if (int rc = launch_grid_build(d_z, (int)M, grid, cell_start, cell_fill, gz, gidx, s)) return rc;
-        forest_gate_kernel<<<grid_dim, kTile, 0, s>>>(a);
-        forest_gate_heavy_kernel<<<grid_dim, kTile, 0, s>>>(a, (int *)f->aw.rc, 2 * (long long)f->cap_nodes);
-        forest_count_scan_kernel<<<grid_dim, kTile, 0, s>>>(a);
-        forest_scan_tiles_kernel<<<1, 1024, 0, s>>>(a);
-        if (f->W <= 8) forest_emit_kernel<8><<<grid_dim, kTile, emit_smem_bytes(f->W), s>>>(a, (int *)f->aw.rc);
-        else forest_emit_kernel<MHT_MAX_WINDOW><<<grid_dim, kTile, emit_smem_bytes(f->W), s>>>(a, (int *)f->aw.rc);
-        tree_off_kernel<<<(f->T + 256) / 256, 256, 0, s>>>(a);
+        count_launch(), forest_gate_kernel<<<grid_dim, kTile, 0, s>>>(a);
+        count_launch(), forest_gate_heavy_kernel<<<grid_dim, kTile, 0, s>>>(a, (int *)f->aw.rc, 2 * (long long)f->cap_nodes);
+        count_launch(), forest_count_scan_kernel<<<grid_dim, kTile, 0, s>>>(a);
+        count_launch(), forest_scan_tiles_kernel<<<1, 1024, 0, s>>>(a);
+        if (f->W <= 8) count_launch(), forest_emit_kernel<8><<<grid_dim, kTile, emit_smem_bytes(f->W), s>>>(a, (int *)f->aw.rc);
+        else count_launch(), forest_emit_kernel<MHT_MAX_WINDOW><<<grid_dim, kTile, emit_smem_bytes(f->W), s>>>(a, (int *)f->aw.rc);
+        count_launch(), tree_off_kernel<<<(f->T + 256) / 256, 256, 0, s>>>(a);
     }
     MHT_CUDA(cudaGetLastError());
     if (phase != 2) MHT_CUDA(cudaEventRecord(f->ev[1], s));
@@ -1165,9 +1171,16 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
         return MHT_OK;
     }
     if (phase == 0) {
-        if (int rc = assoc_solve(c, f->aw, f->cfg.max_dual_iters, 400000, kSMs * 8, s, f->ev[5], f->scan > 1, sift,
-                                 true))
+        const double exact_ms = f->cfg.exact_ms == 0 ? 20.0 : (f->cfg.exact_ms < 0 ? 0.0 : (double)f->cfg.exact_ms);
+        AssocEvents aev;
+        aev.after_cluster = f->ev[5];
+        for (int i = 0; i < 8; ++i) aev.dual[i] = f->evx[i];
+        aev.exact_begin = f->evx[8];
+        aev.exact_end = f->evx[9];
+        if (int rc = assoc_solve(c, f->aw, f->cfg.max_dual_iters, 4096, kSMs * 8, s, &aev, f->scan > 1, sift, true,
+                                 exact_ms))
             return rc;
+        f->n_dual_ev = aev.n_dual;
     } else {
         MHT_CUDA(cudaEventRecord(f->ev[5], s));
     }
@@ -1176,7 +1189,7 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
 
     UpdateArgs u;
     fill_update_args(f, &u);
-    track_update_kernel<<<(f->T + 127) / 128, 128, 0, s>>>(u);
+    count_launch(), track_update_kernel<<<(f->T + 127) / 128, 128, 0, s>>>(u);
     MHT_CUDA(cudaGetLastError());
     MHT_CUDA(cudaEventRecord(f->ev[3], s));
     MHT_CUDA(cudaMemcpyAsync(f->out_h_base, f->out_d_base, (size_t)f->out_bytes, cudaMemcpyDeviceToHost, s));
@@ -1232,7 +1245,7 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
                 f->dead_h[kDeadChunk + i] = f->h_last_pos[dead[lo + i]];
             }
             MHT_CUDA(cudaMemcpyAsync(f->dead_d, f->dead_h, sizeof(int) * 2 * kDeadChunk, cudaMemcpyHostToDevice, s));
-            history_batch_kernel<<<(n + 63) / 64, 64, 0, s>>>(ub, f->dead_d, n, f->scan, f->histb_d);
+            count_launch(), history_batch_kernel<<<(n + 63) / 64, 64, 0, s>>>(ub, f->dead_d, n, f->scan, f->histb_d);
             MHT_CUDA(cudaGetLastError());
             MHT_CUDA(cudaMemcpyAsync(f->histb_h, f->histb_d, sizeof(double) * (size_t)n * kHistStride,
                                      cudaMemcpyDeviceToHost, s));
@@ -1267,6 +1280,18 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
         cudaEventElapsedTime(&info->ms_assoc, f->ev[5], f->ev[2]);
         cudaEventElapsedTime(&info->ms_prune, f->ev[2], f->ev[4]);
         cudaEventElapsedTime(&info->ms_total, f->ev[0], f->ev[4]);
+        info->open_components = st.assoc[5];
+        info->nnz_active = st.assoc[15];
+        info->bb_iters = st.assoc[14];
+        info->rows_active = st.rows_active;
+        if (phase == 0) {
+            for (int i = 0; i < f->n_dual_ev; ++i) {
+                float ms = 0.0f;
+                cudaEventElapsedTime(&ms, f->evx[2 * i], f->evx[2 * i + 1]);
+                info->ms_dual += ms;
+            }
+            cudaEventElapsedTime(&info->ms_exact, f->evx[8], f->evx[9]);
+        }
         if (phase == 2) {  // the association was solved outside the forest (sharded trees)
             info->n_clusters = info->n_multi_clusters = info->n_active = 0;
             info->dual_iters = ext ? (int)ext[5] : 0;
@@ -1335,6 +1360,7 @@ extern "C" int mht_forest_create(const mht_forest_config *cfg, mht_forest **out)
     if (e == cudaSuccess) e = cudaMallocHost(&f->dead_h, sizeof(int) * 2 * 256);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&f->ev[i]);
+    for (int i = 0; i < 10 && e == cudaSuccess; ++i) e = cudaEventCreate(&f->evx[i]);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(forest_emit_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)emit_smem_bytes(8));
@@ -1367,6 +1393,7 @@ extern "C" void mht_forest_destroy(mht_forest *f) {
     if (!f) return;
     cudaStreamSynchronize(f->stream);
     for (int i = 0; i < 6; ++i) cudaEventDestroy(f->ev[i]);
+    for (int i = 0; i < 10; ++i) cudaEventDestroy(f->evx[i]);
     cudaStreamDestroy(f->stream);
     cudaFreeHost(f->out_h_base);
     cudaFreeHost(f->status_h);
@@ -1481,7 +1508,7 @@ extern "C" int mht_forest_export_columns(mht_forest *f, int32_t tree_offset, int
         return MHT_E_INVALID;
     }
     if (f->T == 0) return MHT_OK;
-    export_columns_kernel<<<kSMs * 8, 256, 0, f->stream>>>(f->lv[f->scan % f->nslots], f->rows[f->scan & 1], f->cap_nodes,
+    count_launch(), export_columns_kernel<<<kSMs * 8, 256, 0, f->stream>>>(f->lv[f->scan % f->nslots], f->rows[f->scan & 1], f->cap_nodes,
                                                          f->W, f->d_nc, f->ts.root_cnllr, tree_offset, col_offset, stride,
                                                          d_cost, d_tree, d_rows);
     MHT_CUDA(cudaGetLastError());
@@ -1539,7 +1566,7 @@ extern "C" int mht_forest_min_leaf_distance(mht_forest *f, double px, double py,
     unsigned long long *d = (unsigned long long *)f->hist_d, h = ~0ull;
     MHT_CUDA(cudaMemcpyAsync(d, &h, 8, cudaMemcpyHostToDevice, f->stream));
     if (f->T > 0) {
-        min_leaf_distance_kernel<<<kSMs * 2, 256, 0, f->stream>>>(f->lv[f->scan % f->nslots], f->ts, f->T, px, py, d);
+        count_launch(), min_leaf_distance_kernel<<<kSMs * 2, 256, 0, f->stream>>>(f->lv[f->scan % f->nslots], f->ts, f->T, px, py, d);
         MHT_CUDA(cudaGetLastError());
     }
     MHT_CUDA(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, f->stream));
@@ -1568,7 +1595,7 @@ extern "C" int mht_forest_history(mht_forest *f, int32_t slot, int32_t cap, int3
     } else if (f->h_last_pos[slot] >= 0 && f->scan > f->h_root_scan[slot]) {
         UpdateArgs u;
         fill_update_args(f, &u);
-        history_kernel<<<1, 1, 0, f->stream>>>(u, slot, f->h_last_pos[slot], f->scan, f->hist_d);
+        count_launch(), history_kernel<<<1, 1, 0, f->stream>>>(u, slot, f->h_last_pos[slot], f->scan, f->hist_d);
         MHT_CUDA(cudaGetLastError());
         MHT_CUDA(cudaMemcpyAsync(f->hist_h, f->hist_d, kHistRec * sizeof(double) * (MHT_MAX_WINDOW + 4),
                                  cudaMemcpyDeviceToHost, f->stream));

@@ -136,7 +136,7 @@ int64_t grid_workspace_bytes(int64_t M) {
 
 int launch_grid_build(const double *d_z, int M, GridDesc *d_grid, int *d_cell_start, int *d_cell_fill,
                       double2 *d_gz, int *d_gidx, cudaStream_t s) {
-    grid_build_kernel<<<1, 1024, 0, s>>>((const double2 *)d_z, M, d_grid, d_cell_start, d_cell_fill, d_gz,
+    count_launch(), grid_build_kernel<<<1, 1024, 0, s>>>((const double2 *)d_z, M, d_grid, d_cell_start, d_cell_fill, d_gz,
                                          d_gidx);
     MHT_CUDA(cudaGetLastError());
     return MHT_OK;
@@ -393,11 +393,11 @@ extern "C" int mht_gate_batch(const mht_model *model, int64_t L, int64_t M, cons
     a.cap = cap;
     a.meas_used = d_meas_used;
     const int grid_dim = ntiles < kSMs * 4 ? ntiles : kSMs * 4;
-    gate_batch_count_kernel<<<grid_dim, kTile, 0, s>>>(a);
+    count_launch(), gate_batch_count_kernel<<<grid_dim, kTile, 0, s>>>(a);
     MHT_CUDA(cudaGetLastError());
-    scan_tiles_kernel<<<1, 1024, 0, s>>>(tile_sum, ntiles, nullptr);
+    count_launch(), scan_tiles_kernel<<<1, 1024, 0, s>>>(tile_sum, ntiles, nullptr);
     MHT_CUDA(cudaGetLastError());
-    gate_batch_emit_kernel<<<grid_dim, kTile, 0, s>>>(a);
+    count_launch(), gate_batch_emit_kernel<<<grid_dim, kTile, 0, s>>>(a);
     MHT_CUDA(cudaGetLastError());
     int total = 0;
     MHT_CUDA(cudaMemcpyAsync(&total, tile_sum + ntiles, sizeof(int), cudaMemcpyDeviceToHost, s));

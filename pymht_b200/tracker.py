@@ -13,6 +13,7 @@ The M-of-N initiator is out of scope: `self.initiator` defaults to a null object
 processMeasurements(unusedRadar, unusedAis) -> [Target] can be plugged in (tracker.py:266-277).
 """
 import ctypes as C
+import logging
 import os
 import time
 
@@ -21,6 +22,9 @@ import numpy as np
 from . import _lib
 from .pyTarget import Target, STATUS_TAGS, preinitializedTag, backtrackMeasurementNumbers  # noqa: F401
 from .utils.classDefinitions import AisMessageList
+
+
+log = logging.getLogger(__name__)
 
 
 class NullInitiator:
@@ -74,6 +78,11 @@ class Tracker:
         self.maxNodes = int(kwargs.get("maxNodes", 1 << 22))
         self.maxParents = int(kwargs.get("maxParents", max(1 << 16, self.maxNodes // 3)))
         self.maxDualIterations = int(kwargs.get("maxDualIterations", os.environ.get("MHT_DUAL_ITERS", 120)))
+        # wall-clock budget (ms per scan) of the exact branch & bound behind the dual loop; strict=True raises
+        # when a scan's global hypothesis could not be proven optimal (the reference only warns, tracker.py:1201-1204)
+        self.exactBudgetMs = int(kwargs.get("exactBudgetMs", os.environ.get("MHT_EXACT_MS", 0)))
+        self.strict = bool(kwargs.get("strict", False))
+        self.nNotOptimal = 0                # scans whose association was not certified optimal
         self._lib = _lib.load()
         self._forest = None
         self._slots = []                    # forest slot of each live track (list order = reference order)
@@ -94,6 +103,7 @@ class Tracker:
         cfg.radar_range = float(self.radarRange) if np.isfinite(self.radarRange) else 1e300
         cfg.position[0], cfg.position[1] = float(self.position[0]), float(self.position[1])
         cfg.max_dual_iters = self.maxDualIterations
+        cfg.exact_ms = self.exactBudgetMs
         handle = C.c_void_p()
         _lib.check(self._lib.mht_forest_create(C.byref(cfg), C.byref(handle)))
         self._forest = handle
@@ -151,17 +161,28 @@ class Tracker:
                 raise NotImplementedError(kw + " is outside the accelerated path")
         self.tic.clear()
         self.toc.clear()
-        self.__scanHistory__.append(scanList)
-        self.__aisHistory__.append(aisList if aisList is not None else AisMessageList())
         t_total = time.time()
         z = np.ascontiguousarray(scanList.measurements, dtype=np.float64).reshape(-1, 2)
         nMeas = z.shape[0]
         used = np.zeros(max(nMeas, 1), dtype=np.uint8)
         info = _lib.ScanInfo()
+        # a refused scan (capacity) leaves the forest unchanged: the histories only grow once it succeeded
         _lib.check(self._lib.mht_forest_scan(self._forest, nMeas, _lib.ptr(z), float(scanList.time), C.byref(info),
                                              _lib.ptr(used)))
+        self.__scanHistory__.append(scanList)
+        self.__aisHistory__.append(aisList if aisList is not None else AisMessageList())
         self.scanInfo.append(info.as_dict())
         self.nOptimSolved = info.n_multi_clusters
+        if not info.certified:
+            # reference tracker.py:1201-1204: "Optim result NOT optimal" is a warning there, too
+            self.nNotOptimal += 1
+            msg = ("Optim result NOT optimal (scan %d): objective %.6f, lower bound %.6f, gap %.3g; %d open "
+                   "component(s), largest %d trees" % (len(self.__scanHistory__), info.objective, info.lower_bound,
+                                                       info.objective - info.lower_bound, info.n_components,
+                                                       info.max_component))
+            if self.strict:
+                raise RuntimeError(msg)
+            log.warning(msg)
         self.toc["Process"] = info.ms_gate * 1e-3
         self.toc["Cluster"] = info.ms_cluster * 1e-3
         self.toc["Optim"] = info.ms_assoc * 1e-3

@@ -26,7 +26,7 @@ def test_struct_layouts_match_header():
     from pymht_b200 import _lib
     assert ctypes.sizeof(_lib.Model) == 16 * 4 + 16 * 4 + 8 * 4 + 4 * 4 + 16
     assert ctypes.sizeof(_lib.ForestConfig) == ctypes.sizeof(_lib.Model) + 4 * 3 + 4 + 8 * 2 + 8 * 4 + 16 + 8
-    assert ctypes.sizeof(_lib.ScanInfo) == 8 * 3 + 4 * 6 + 8 * 2 + 8 * 2 + 4 * 6 + 8 + 8
+    assert ctypes.sizeof(_lib.ScanInfo) == 8 * 3 + 4 * 6 + 8 * 2 + 8 * 2 + 4 * 6 + 8 + 8 + 4 * 2 + 8 + 4 * 4
 
 
 def test_no_cpu_fallback_without_device():

@@ -200,32 +200,35 @@ def test_tracker_replays_reference_golden(name):
 @pytest.mark.parametrize("name", ["cfg3_head", "cfg3_lowclutter"])
 def test_tracker_cfg3_vs_reference(name):
     """1k targets: the scans the reference can still finish (cfg3_head: 5k measurements, lambda=1e-3, 2 scans;
-    cfg3_lowclutter: lambda=1e-4, 3 scans).  While every solve is certified the tracks must be IDENTICAL to the
-    reference's (cfg3_head scan 1, cfg3_lowclutter scans 1-2: the 285-tree cluster of scan 2 is solved exactly).  From the first uncertified scan on (a >100-tree cluster with an LP gap: the depth-first
-    repair gives up) the selection is a feasible near-optimum: >= 94 % of the common tracks
-    still carry the reference's measurement history, <= 2 % of the tracks differ in termination, and the
-    objective stays within 0.5 % of the certified lower bound."""
-    certified_so_far = True
-    for k, g, pre, trk, nodes, hist, info in _replay_tracker(name, maxTargets=1024, maxNodes=1 << 20):
+    cfg3_lowclutter: lambda=1e-4, 3 scans).  The global hypothesis must be PROVEN optimal and the tracks IDENTICAL to
+    the reference's -- ids, measurement histories -- on every scan, including the clusters whose LP relaxation has
+    a gap (cfg3_head scan 2: 279 trees, gap 0.74; closed by the branch & bound of csrc/bb_core.h).
+    One exception, stated, not hidden: cfg3_lowclutter scan 3 holds a 787-tree cluster with an LP gap of 6.0 that
+    HiGHS itself needs ~100 s (cuts + strong branching) to close; the exact search's budget here is 30 s.  If it does
+    not finish, the scan must still be a feasible near-optimum (reported uncertified, bound gap printed) and the
+    test says so -- see DESIGN.md section 4."""
+    for k, g, pre, trk, nodes, hist, info in _replay_tracker(name, maxTargets=1024, maxNodes=1 << 20,
+                                                             exactBudgetMs=30000):
         ids, want = [n.ID for n in nodes], list(g[pre + "ids"])
         H = g[pre + "hist"]
         common = [i for i in ids if i in set(want)]
         same = sum(hist[ids.index(i)] == list(H[want.index(i), :len(hist[ids.index(i)])]) for i in common)
-        certified_so_far = certified_so_far and bool(info["certified"])
         print(name, "scan", k + 1, {kk: info[kk] for kk in ("n_parents", "n_children", "n_clusters", "certified",
                                                            "dual_iters", "n_candidates", "max_component", "bb_nodes",
                                                            "lower_bound", "objective", "ms_gate", "ms_assoc")})
         print("  identical measurement histories: %d / %d common tracks (%d ours, %d reference)" % (
             same, len(common), len(ids), len(want)))
-        if name == "cfg3_lowclutter" and k < 2:
-            assert certified_so_far, (name, k, info)
-        if certified_so_far:
+        hard = name == "cfg3_lowclutter" and k == 2
+        if info["certified"] or not hard:
+            assert info["certified"] == 1, (name, k, info)
             assert ids == want
             assert same == len(want)
         else:
+            print("  NOT CERTIFIED (787-tree cluster, LP gap 6.0): objective %.4f, bound %.4f" % (
+                info["objective"], info["lower_bound"]))
             assert len(set(ids) ^ set(want)) <= 0.02 * len(want)
             assert same >= 0.94 * len(common)
-            assert info["objective"] - info["lower_bound"] <= 5e-3 * abs(info["lower_bound"]) + 1e-9 or k >= 2
+            assert info["objective"] - info["lower_bound"] <= 5e-3 * abs(info["lower_bound"]) + 1e-9
 
 
 def test_large_random_forest_properties():
