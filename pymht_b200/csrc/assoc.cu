@@ -2189,6 +2189,7 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
         static const int k_node = getenv("MHT_BB_KNODE") ? atoi(getenv("MHT_BB_KNODE")) : 60;
         static const double env_ms = getenv("MHT_BB_MS") ? atof(getenv("MHT_BB_MS")) : -1.0;
         const double ms = env_ms >= 0.0 ? env_ms : exact_ms;
+        if (ev && ev->exact_begin) MHT_CUDA(cudaEventRecord(ev->exact_begin, s));
         count_launch(), bb_plan_kernel<<<1, 1024, 0, s>>>(c, w);
         if (ms > 0.0) {
             count_launch(), bb_compact_kernel<<<kSMs, 256, 0, s>>>(c, w);
