@@ -52,7 +52,11 @@ class _Anything:
 def _stub_module(name, **attrs):
     mod = types.ModuleType(name)
     mod.__dict__.update(attrs)
-    mod.__getattr__ = lambda attr: _Anything()  # PEP 562 module-level fallback
+    def _fallback(attr):  # PEP 562 module-level fallback; dunders (__file__, __path__ ...) stay absent so that
+        if attr.startswith("__") and attr.endswith("__"):   # inspect / importlib treat the stub like a builtin
+            raise AttributeError(attr)
+        return _Anything()
+    mod.__getattr__ = _fallback
     sys.modules[name] = mod
     return mod
 

@@ -36,7 +36,7 @@ constexpr double kFix = 17179869184.0;  // 2^34
 constexpr int kPatience = 10;
 constexpr double kShrink = 0.7;
 constexpr int kMaxCandPerTree = 2048;   // per-tree candidate list limit (insertion sort, one thread)
-constexpr int kDomMax = 192;             // dominance reduction only for lists up to this length
+constexpr int kDomMax = 64;              // sorting / dominance reduction / enumeration only for lists up to this length
 constexpr int kGreedyRounds = 40;
 constexpr int kGreedyEvery = 40;
 constexpr int kStallStop = 60;
@@ -987,7 +987,7 @@ __global__ void cand_sort_kernel(ColView c, AssocWork w) {
     if (w.info[6]) return;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
         const int cnt = w.cand_cnt[t];
-        if (cnt == 0) continue;
+        if (cnt == 0 || cnt > kDomMax) continue;   // long lists stay unsorted: only the branch & bound sees them
         int *v = w.cand_col + w.cand_off[t];
         for (int i = 1; i < cnt; ++i) {
             const int key = v[i];
@@ -1021,10 +1021,12 @@ __global__ void contest_reset_kernel(AssocWork w) {
 // also used for the component union (uf != null): trees sharing a row among surviving candidates
 __global__ void contest_mark_kernel(ColView c, AssocWork w, int *uf) {
     if (w.info[6]) return;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (int t = warp; t < c.n_trees; t += nwarp) {
         const int cnt = w.cand_cnt[t];
         const int *v = w.cand_col + w.cand_off[t];
-        for (int i = 0; i < cnt; ++i) {
+        for (int i = lane; i < cnt; i += 32) {
             const int j = v[i];
             for (int k = 0; k < c.width; ++k) {
                 const int r = c.rows[(long long)k * c.stride + j];
@@ -1400,6 +1402,9 @@ __global__ void __launch_bounds__(32) branch_bound_kernel(ColView c, AssocWork w
         w.bbw.comp_state[comp] = 0;
         if (k > kDfsMaxTrees) continue;
         int *trees = w.comp_trees + off;
+        bool lists_short = true;
+        for (int i = 0; i < k; ++i) lists_short = lists_short && w.cand_cnt[trees[i]] <= kDomMax;
+        if (!lists_short) continue;
         // deterministic order: fewest candidates first, then tree index
         for (int i = 1; i < k; ++i) {
             const int key = trees[i];
@@ -1510,7 +1515,7 @@ __global__ void __launch_bounds__(32) branch_bound_kernel(ColView c, AssocWork w
 // node evaluation, every CTA of the grid serving one shared node pool
 // ------------------------------------------------------------------------------------------------
 // single CTA: which components still need the search, offsets of their compacted cores
-__global__ void __launch_bounds__(1024, 1) bb_plan_kernel(ColView c, AssocWork w) {
+__global__ void __launch_bounds__(1024, 1) bb_plan_kernel(ColView c, AssocWork w, int max_cols_now) {
     BBWork &b = w.bbw;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 16; ++i) b.hdr[i] = 0;
@@ -1534,7 +1539,7 @@ __global__ void __launch_bounds__(1024, 1) bb_plan_kernel(ColView c, AssocWork w
         for (int k = 0; k < ncomp; ++k) {
             if (b.comp_state[k]) continue;
             const int nT = w.comp_off[k + 1] - w.comp_off[k], nC = w.cl_stall[k];
-            if (nC > b.max_cols || nT > b.max_trees || n >= kBBMaxNodes / 4) continue;   // stays open: uncertified
+            if (nC > b.max_cols || nC > max_cols_now || nT > b.max_trees || n >= kBBMaxNodes / 4) continue;   // stays open: uncertified
             bb::Comp &p = b.comps[n];
             p.nC = nC;
             p.nT = nT;
@@ -2173,14 +2178,15 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
     count_launch(), cand_fill_kernel<<<grid_dim, 256, 0, s>>>(c, w);
     {
         const int tb = (c.n_trees + 127) / 128, rb = (c.n_rows + 255) / 256 < 1024 ? (c.n_rows + 255) / 256 : 1024;
+        const int wb = (c.n_trees + 7) / 8;
         count_launch(), cand_sort_kernel<<<tb, 128, 0, s>>>(c, w);
-        for (int round = 0; round < 3; ++round) {
+        for (int round = 0; round < 2; ++round) {
             count_launch(), contest_reset_kernel<<<rb, 256, 0, s>>>(w);
-            count_launch(), contest_mark_kernel<<<tb, 128, 0, s>>>(c, w, nullptr);
+            count_launch(), contest_mark_kernel<<<wb, 256, 0, s>>>(c, w, nullptr);
             count_launch(), cand_dominance_kernel<<<tb, 128, 0, s>>>(c, w);
         }
         count_launch(), contest_reset_kernel<<<rb, 256, 0, s>>>(w);
-        count_launch(), contest_mark_kernel<<<tb, 128, 0, s>>>(c, w, w.comp_uf);
+        count_launch(), contest_mark_kernel<<<wb, 256, 0, s>>>(c, w, w.comp_uf);
     }
     count_launch(), comp_build_kernel<<<1, 1024, 0, s>>>(c, w);
     count_launch(), branch_bound_kernel<<<kSMs * 4, 32, 0, s>>>(c, w, bb_budget, g_fscratch);
@@ -2190,7 +2196,10 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
         static const double env_ms = getenv("MHT_BB_MS") ? atof(getenv("MHT_BB_MS")) : -1.0;
         const double ms = env_ms >= 0.0 ? env_ms : exact_ms;
         if (ev && ev->exact_begin) MHT_CUDA(cudaEventRecord(ev->exact_begin, s));
-        count_launch(), bb_plan_kernel<<<1, 1024, 0, s>>>(c, w);
+        // a dual iteration on n columns costs ~n / 4e9 s in one CTA: components the time box cannot even evaluate
+        // a few hundred times are left alone (they stay open, the scan is reported uncertified)
+        const double cols_now = ms * 4000.0;
+        count_launch(), bb_plan_kernel<<<1, 1024, 0, s>>>(c, w, cols_now > 1e9 ? 1000000000 : (int)cols_now);
         if (ms > 0.0) {
             count_launch(), bb_compact_kernel<<<kSMs, 256, 0, s>>>(c, w);
             count_launch(), bb_root_kernel<<<kSMs, 256, 0, s>>>(c, w, ms);

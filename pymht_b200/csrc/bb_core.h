@@ -79,6 +79,7 @@ struct EvalResult {
     double bound;                // best bound seen (1e300: infeasible)
     int bt, br;                  // branching pair (-1: none)
     int solved;                  // 1 = conflict-free choices met the bound (node closed)
+    int aborted;                 // 1 = the deadline passed during the iterations (bound still valid)
     int iters;
 };
 
@@ -166,13 +167,17 @@ template <class Ctx>
 BB_HD inline void evaluate(Ctx &c, const Comp &p, Scratch &s, int K, EvalResult &res) {
     double bestL = -1e300, theta = 1.0;
     int stall = 0, it = 0;
-    bool solved = false, infeasible = false;
+    bool solved = false, infeasible = false, aborted = false;
     const int half = K / 2;
     for (int j = c.tid(); j < p.nC; j += c.nthr()) s.freq[j] = 0;
     for (int r = c.tid(); r < p.nR; r += c.nthr()) s.ubest[r] = s.u[r];
     for (int t = c.tid(); t < p.nT; t += c.nthr()) s.best_targ[t] = -1;
     c.sync();
     for (it = 0; it < K; ++it) {
+        if ((it & 15) == 15 && bcast0(c, c.expired() ? 1 : 0)) {
+            aborted = true;
+            break;
+        }
         for (int t = c.tid(); t < p.nT; t += c.nthr()) {
             s.tmin[t] = kInfKey;
             s.targ[t] = -1;
@@ -267,13 +272,14 @@ BB_HD inline void evaluate(Ctx &c, const Comp &p, Scratch &s, int K, EvalResult 
     res.iters = it;
     res.bt = res.br = -1;
     res.solved = solved ? 1 : 0;
+    res.aborted = aborted ? 1 : 0;
     if (infeasible) {
         res.bound = 1e300;
         return;
     }
     res.bound = bestL;
     const double ub = read_ub(c, p);
-    if (solved || bestL >= ub - kPruneEps) return;
+    if (solved || aborted || bestL >= ub - kPruneEps) return;
 
     // ---- reduced costs at the best iterate: fixing + tree minima ----
     for (int r = c.tid(); r < p.nR; r += c.nthr()) s.u[r] = s.ubest[r];
@@ -575,6 +581,13 @@ BB_HD inline int expand(Ctx &c, const Comp *comps, Pool &pl, int cur, Scratch &s
         double b = res.bound;
         if (!root && b < pbound) b = pbound;      // a child is never weaker than its parent
         if (res.solved || b >= ub - kPruneEps) continue;
+        if (res.aborted) {                         // out of time inside the node: its subtree stays unexplored
+            if (c.tid() == 0) {
+                *(volatile int *)pl.stop = 1;
+                *(volatile int *)&pl.comp_unproven[ci] = 1;
+            }
+            continue;
+        }
         if (res.bt < 0) {                          // open but nothing to branch on (numerical corner): give up on it
             if (c.tid() == 0) *(volatile int *)&pl.comp_unproven[ci] = 1;
             continue;
