@@ -1056,49 +1056,57 @@ __device__ __forceinline__ bool contested_subset(const ColView &c, const int *ro
     return true;
 }
 
-__global__ void cand_dominance_kernel(ColView c, AssocWork w) {
+// one WARP per tree: lane = the candidate b under test (lists are at most kDomMax = 64 long: two per lane)
+__global__ void __launch_bounds__(256) cand_dominance_kernel(ColView c, AssocWork w) {
     if (w.info[6]) return;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (int t = warp; t < c.n_trees; t += nwarp) {
         const int cnt = w.cand_cnt[t];
         if (cnt < 2 || cnt > kDomMax) continue;
         int *v = w.cand_col + w.cand_off[t];
-        unsigned long long drop[(kDomMax + 63) / 64] = {0ull};
-        for (int ib = 0; ib < cnt; ++ib) {
-            const int b = v[ib];
-            const double cb = col_cost(c, b, t);
-            for (int ia = 0; ia < cnt; ++ia) {
-                if (ia == ib) continue;
-                const int a = v[ia];
-                const double ca = col_cost(c, a, t);
-                if (!(ca < cb || (ca == cb && a > b))) continue;   // ties: the later leaf wins, like the reference
-                if (contested_subset(c, w.row_cont, a, b)) {
-                    drop[ib >> 6] |= 1ull << (ib & 63);
-                    break;
+        unsigned long long drop = 0ull;
+        for (int half = 0; half < 2; ++half) {
+            const int ib = lane + 32 * half;
+            bool dominated = false;
+            if (ib < cnt) {
+                const int b = v[ib];
+                const double cb = col_cost(c, b, t);
+                for (int ia = 0; ia < cnt && !dominated; ++ia) {
+                    if (ia == ib) continue;
+                    const int a = v[ia];
+                    const double ca = col_cost(c, a, t);
+                    if (!(ca < cb || (ca == cb && a > b))) continue;   // ties: the later leaf wins, like the reference
+                    dominated = contested_subset(c, w.row_cont, a, b);
                 }
             }
+            drop |= (unsigned long long)__ballot_sync(0xffffffffu, dominated) << (32 * half);
         }
         // the incumbent must stay inside the lists (components are only independent over listed columns):
         // if it was dominated, a surviving dominator replaces it -- feasible and not more expensive
-        const int inc = w.sel[t];
-        for (int ib = 0; ib < cnt; ++ib) {
-            if (v[ib] != inc || !(drop[ib >> 6] >> (ib & 63) & 1ull)) continue;
-            const double cb = col_cost(c, inc, t);
-            bool replaced = false;
-            for (int ia = 0; ia < cnt && !replaced; ++ia) {
-                if (drop[ia >> 6] >> (ia & 63) & 1ull) continue;
-                const int a = v[ia];
-                const double ca = col_cost(c, a, t);
-                if ((ca < cb || (ca == cb && a > inc)) && contested_subset(c, w.row_cont, a, inc)) {
-                    w.sel[t] = a;
-                    replaced = true;
+        if (lane == 0) {
+            const int inc = w.sel[t];
+            for (int ib = 0; ib < cnt; ++ib) {
+                if (v[ib] != inc || !(drop >> ib & 1ull)) continue;
+                const double cb = col_cost(c, inc, t);
+                bool replaced = false;
+                for (int ia = 0; ia < cnt && !replaced; ++ia) {
+                    if (drop >> ia & 1ull) continue;
+                    const int a = v[ia];
+                    const double ca = col_cost(c, a, t);
+                    if ((ca < cb || (ca == cb && a > inc)) && contested_subset(c, w.row_cont, a, inc)) {
+                        w.sel[t] = a;
+                        replaced = true;
+                    }
                 }
+                if (!replaced) drop &= ~(1ull << ib);
             }
-            if (!replaced) drop[ib >> 6] &= ~(1ull << (ib & 63));
+            int n = 0;
+            for (int i = 0; i < cnt; ++i)
+                if (!(drop >> i & 1ull)) v[n++] = v[i];
+            w.cand_cnt[t] = n;
         }
-        int n = 0;
-        for (int i = 0; i < cnt; ++i)
-            if (!(drop[i >> 6] >> (i & 63) & 1ull)) v[n++] = v[i];
-        w.cand_cnt[t] = n;
+        __syncwarp();
     }
 }
 
@@ -1576,7 +1584,6 @@ __global__ void __launch_bounds__(1024, 1) bb_plan_kernel(ColView c, AssocWork w
 __global__ void __launch_bounds__(256) bb_compact_kernel(ColView c, AssocWork w) {
     BBWork &b = w.bbw;
     const int n = b.hdr[0];
-    __shared__ double s_ub;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         bb::Comp &p = b.comps[i];
         const int k = b.comp_slot[i];
@@ -1584,18 +1591,39 @@ __global__ void __launch_bounds__(256) bb_compact_kernel(ColView c, AssocWork w)
         int *tstart = (int *)p.tstart;
         const long long col_off = p.cost - b.c_cost;
         const long long tree_off = p.best_sel - b.best_sel;
-        if (threadIdx.x == 0) {
+        {   // tstart = exclusive prefix of the candidate counts, ub = cost of the incumbent (fixed summation order)
+            __shared__ int s_cnt[256];
+            __shared__ double s_part[256];
+            const int per = (p.nT + 255) / 256;
+            const int lo = min(p.nT, (int)threadIdx.x * per), hi = min(p.nT, lo + per);
             int acc = 0;
             double ub = 0.0;
-            for (int t = 0; t < p.nT; ++t) {
+            for (int t = lo; t < hi; ++t) {
+                acc += w.cand_cnt[trees[t]];
+                ub += col_cost(c, w.sel[trees[t]], trees[t]);
+                b.t_gtree[tree_off + t] = trees[t];
+            }
+            s_cnt[threadIdx.x] = acc;
+            s_part[threadIdx.x] = ub;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int run = 0;
+                double tot = 0.0;
+                for (int q = 0; q < 256; ++q) {
+                    const int v = s_cnt[q];
+                    s_cnt[q] = run;
+                    run += v;
+                    tot += s_part[q];
+                }
+                tstart[p.nT] = run;
+                b.ub_key[i] = bb::key_of(tot);
+            }
+            __syncthreads();
+            acc = s_cnt[threadIdx.x];
+            for (int t = lo; t < hi; ++t) {
                 tstart[t] = acc;
                 acc += w.cand_cnt[trees[t]];
-                b.t_gtree[tree_off + t] = trees[t];
-                ub += col_cost(c, w.sel[trees[t]], trees[t]);
             }
-            tstart[p.nT] = acc;
-            s_ub = ub;
-            b.ub_key[i] = bb::key_of(ub);
         }
         __syncthreads();
         // columns: warp per tree, lanes over its candidates; rows marked for numbering
@@ -1765,6 +1793,36 @@ struct DeviceCtx {
         __syncthreads();
         return s;
     }
+    // sums of a and b, maximum of m, and thread 0's x to everybody: one pair of barriers
+    __device__ void reduce(double &a, double &b, long long &m, unsigned long long &x) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+            const long long y = __shfl_xor_sync(0xffffffffu, m, o);
+            m = y > m ? y : m;
+        }
+        const int nw = (int)(blockDim.x >> 5);
+        if ((threadIdx.x & 31) == 0) {
+            red_d[threadIdx.x >> 5] = a;
+            red_d[32 + (threadIdx.x >> 5)] = b;
+            red_l[threadIdx.x >> 5] = m;
+        }
+        if (threadIdx.x == 0) *word = x;
+        __syncthreads();
+        double sa = 0.0, sb = 0.0;
+        long long sm = red_l[0];
+        for (int i = 0; i < nw; ++i) {
+            sa += red_d[i];
+            sb += red_d[32 + i];
+            sm = red_l[i] > sm ? red_l[i] : sm;
+        }
+        x = *word;
+        __syncthreads();
+        a = sa;
+        b = sb;
+        m = sm;
+    }
     __device__ unsigned long long bcast(unsigned long long v) {
         if (threadIdx.x == 0) *word = v;
         __syncthreads();
@@ -1813,7 +1871,7 @@ __host__ __device__ inline long long bb_scratch_bytes(long long max_cols, long l
 
 __global__ void __launch_bounds__(kBBThreads, 1) bb_search_kernel(AssocWork w, int K_root, int K_node, int max_nodes) {
     extern __shared__ __align__(16) unsigned char bb_smem[];
-    __shared__ double red_d[32];
+    __shared__ double red_d[64];
     __shared__ long long red_l[32];
     __shared__ unsigned long long word;
     const BBWork &b = w.bbw;
@@ -2183,7 +2241,7 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
         for (int round = 0; round < 2; ++round) {
             count_launch(), contest_reset_kernel<<<rb, 256, 0, s>>>(w);
             count_launch(), contest_mark_kernel<<<wb, 256, 0, s>>>(c, w, nullptr);
-            count_launch(), cand_dominance_kernel<<<tb, 128, 0, s>>>(c, w);
+            count_launch(), cand_dominance_kernel<<<wb, 256, 0, s>>>(c, w);
         }
         count_launch(), contest_reset_kernel<<<rb, 256, 0, s>>>(w);
         count_launch(), contest_mark_kernel<<<wb, 256, 0, s>>>(c, w, w.comp_uf);

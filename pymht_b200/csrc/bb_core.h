@@ -87,6 +87,7 @@ struct EvalResult {
 //      void amin64(unsigned long long*, unsigned long long); void amax(int*, int); void aadd(int*, int);
 //      double sum(double); long long maxll(long long);   (block-wide, every thread gets the result)
 //      unsigned long long bcast(unsigned long long)      (thread 0's value to every thread)
+//      void reduce(double &a, double &b, long long &m, unsigned long long &x)   a, b summed, m maximised, x = thread 0's
 //      int acas(int*, int cmp, int val); void fence();
 //      bool bind(const Comp&, Scratch&)  point the scratch at memory that holds the component (false: too big)
 //      void backoff(); bool expired()    (thread 0's view; callers broadcast it)
@@ -219,12 +220,12 @@ BB_HD inline void evaluate(Ctx &c, const Comp &p, Scratch &s, int K, EvalResult 
             }
             if (it >= half) s.freq[j] += 1;
         }
-        if (c.maxll(dead)) {
+        unsigned long long xk = 0;
+        c.reduce(lsum, csum, dead, xk);
+        if (dead) {
             infeasible = true;
             break;
         }
-        lsum = c.sum(lsum);
-        csum = c.sum(csum);
         double usum = 0.0, nrm = 0.0;
         long long worst = 0;
         for (int r = c.tid(); r < p.nR; r += c.nthr()) {
@@ -235,11 +236,11 @@ BB_HD inline void evaluate(Ctx &c, const Comp &p, Scratch &s, int K, EvalResult 
             nrm += (double)(g * g);
             if (s.usage[r] > worst) worst = s.usage[r];
         }
-        usum = c.sum(usum);
-        nrm = c.sum(nrm);
-        worst = c.maxll(worst);
+        // the incumbent may have been improved by another worker: thread 0 reads it, everybody gets the same value
+        if (c.tid() == 0) xk = *(volatile unsigned long long *)p.ub_key;
+        c.reduce(usum, nrm, worst, xk);
         const double L = lsum - usum;
-        double ub = read_ub(c, p);
+        double ub = of_key(xk);
         if (worst <= 1 && csum < ub - 1e-12) {
             offer_incumbent(c, p, s, csum);
             ub = read_ub(c, p);

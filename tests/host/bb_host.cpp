@@ -17,6 +17,7 @@ struct HostCtx {
     double sum(double v) { return v; }
     long long maxll(long long v) { return v; }
     unsigned long long bcast(unsigned long long v) { return v; }
+    void reduce(double &, double &, long long &, unsigned long long &) {}
     int acas(int *p, int cmp, int val) { const int old = *p; if (old == cmp) *p = val; return old; }
     void fence() {}
     void backoff() {}
