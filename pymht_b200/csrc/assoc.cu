@@ -646,8 +646,10 @@ __global__ void __launch_bounds__(1024, 1) greedy_finish_kernel(ColView c, Assoc
 // phases): `iters` subgradient iterations, a greedy primal pass every kGreedyEvery iterations whose
 // bidding rounds stop as soon as every tree is committed.  Replaces ~7 launches per iteration.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dual_loop_persistent_kernel(ColView c, AssocWork w, int iters, int greedy_every) {
+__global__ void __launch_bounds__(256) dual_loop_persistent_kernel(ColView c, AssocWork w, int iters, int greedy_every,
+                                                                   const int *declined) {
     cg::grid_group grid = cg::this_grid();
+    if (declined && *declined == 0) return;   // the cluster version ran this loop
     for (int it = 0; it < iters; ++it) {
         if (((volatile int *)w.info)[0]) break;  // uniform: written before the last grid.sync
         if (it % greedy_every == 0) {
@@ -682,6 +684,186 @@ __global__ void __launch_bounds__(256) dual_loop_persistent_kernel(ColView c, As
         grid.sync();
         du_apply_finish_body(c, w);
         grid.sync();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same loop inside ONE thread-block cluster (16 CTAs x 1024 threads on sm_100): the iteration is latency
+// bound -- a few tens of thousands of columns, six dependent phases -- so what it needs is a cheap barrier and
+// short load chains, not more threads.  Versus the grid version above:
+//   * barrier.cluster (hardware, ~0.2 us) instead of the cooperative-groups grid barrier (~1.8 us each);
+//   * every CTA keeps its slice of the iterated columns {cost, tree, rows} resident in shared memory for the whole
+//     launch (the column set is fixed between pricing passes), so the reduced-cost pass is shared-memory reads +
+//     ONE hop to the multipliers, and the argmin pass needs no column data at all;
+//   * every thread keeps the (row, cluster) pairs it owns in registers, so the row phases are one hop as well.
+// Same arithmetic, same fixed-point sums: the result is bit-identical to the grid version.  The kernel declines
+// (info[kAssocInfo - 1] bit 30 stays clear -> the grid version runs) when the slice does not fit.
+// ------------------------------------------------------------------------------------------------
+constexpr int kClusterCtas = 16;
+constexpr int kClusterThreads = 1024;
+constexpr int kClusterRowsPerThread = 6;    // rows with a multiplier: <= 16 * 1024 * 6
+
+__host__ __device__ inline size_t cluster_slice_bytes(int nc, int W) {
+    return (size_t)nc * (8 + 8 + 4 + 4 * (size_t)W) + 64;
+}
+
+__global__ void __launch_bounds__(kClusterThreads, 1)
+dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, int nc_cap, int *declined) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char dl_smem[];
+    const int n = *c.n_ptr;
+    const int nr = *w.row_n;
+    const int nctas = (int)gridDim.x, nth = nctas * (int)blockDim.x;
+    const int gtid = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int per = (n + nctas - 1) / nctas;
+    // uniform over the cluster: every CTA sees the same n / nr
+    if (per > nc_cap || nr > nth * kClusterRowsPerThread || c.n_trees > nth) {
+        if (gtid == 0) *declined = 1;
+        return;
+    }
+    if (gtid == 0) *declined = 0;
+    const int lo = min(n, (int)blockIdx.x * per), hi = min(n, lo + per), nc = hi - lo;
+    double *s_cost = (double *)dl_smem;
+    double *s_rc = s_cost + nc_cap;
+    int *s_tree = (int *)(s_rc + nc_cap);
+    int *s_rows = s_tree + nc_cap;             // [W][nc_cap]
+    for (int k = threadIdx.x; k < nc; k += blockDim.x) {
+        const int j = c.idx ? c.idx[lo + k] : lo + k;
+        const int t = c.tree[j];
+        s_tree[k] = t;
+        s_cost[k] = col_cost(c, j, t);
+        for (int q = 0; q < c.width; ++q) s_rows[q * nc_cap + k] = c.rows[(long long)q * c.stride + j];
+    }
+    // rows this thread owns for the whole launch: (row, cluster label); the label of a row never changes
+    int my_r[kClusterRowsPerThread], my_cl[kClusterRowsPerThread];
+    const int nq = (nr + nth - 1) / nth;
+#pragma unroll
+    for (int q = 0; q < kClusterRowsPerThread; ++q) {
+        const int i = gtid + q * nth;
+        my_r[q] = -1;
+        my_cl[q] = 0;
+        if (q < nq && i < nr) {
+            my_r[q] = w.row_list[i];
+            my_cl[q] = w.uf[w.row_owner[my_r[q]]];
+        }
+    }
+    __syncthreads();
+    const int nc_round = (nc + 31) & ~31;
+    for (int it = 0; it < iters; ++it) {
+        if (((volatile int *)w.info)[0]) break;  // uniform: written before the last cluster barrier
+        if (it % greedy_every == 0) {
+            dual_rc_body<false>(c, w);
+            cluster.sync();
+            for (int mode = 0; mode < (it ? 2 : 1); ++mode) {
+                if (gtid == 0) w.stall_ctr[3] = mode;
+                greedy_init_body(c, w, w.tstart);
+                cluster.sync();
+                for (int r = 0; r < kGreedyRounds; ++r) {
+                    if (((volatile int *)w.info)[2] == 0) break;
+                    greedy_prop_body(c, w);
+                    cluster.sync();
+                    greedy_arg_body(c, w);
+                    cluster.sync();
+                    if (blockIdx.x == 0) greedy_commit_body(c, w);
+                    cluster.sync();
+                }
+                if (blockIdx.x == 0) greedy_finish_body(c, w, w.tstart);
+                cluster.sync();
+            }
+        }
+        // ---- reduced costs + per-tree minimum: shared-memory slice, one hop to the multipliers ----
+        for (int k = threadIdx.x; k < nc_round; k += blockDim.x) {
+            int t = -1;
+            unsigned long long key = kKeyInf;
+            if (k < nc) {
+                t = s_tree[k];
+                if (!w.tdone[t]) {
+                    double v = s_cost[k];
+                    for (int q = 0; q < c.width; ++q) {
+                        const int r = s_rows[q * nc_cap + k];
+                        if (r >= 0) v += w.u[r];
+                    }
+                    s_rc[k] = v;
+                    key = f64_key(v);
+                } else {
+                    t = -1;
+                }
+            }
+            const bool head = warp_run_min(t, key);
+            if (head && t >= 0) atomicMin(&w.tmin[t], key);
+        }
+        cluster.sync();
+        // ---- argmin (ties -> last column) ----
+        for (int k = threadIdx.x; k < nc; k += blockDim.x) {
+            const int t = s_tree[k];
+            if (w.tdone[t]) continue;
+            if (f64_key(s_rc[k]) == w.tmin[t]) atomicMax(&w.targ[t], c.idx ? c.idx[lo + k] : lo + k);
+        }
+        cluster.sync();
+        du_trees_body(c, w);
+        cluster.sync();
+        // ---- rows: subgradient, norms (this thread's rows) ----
+        if (!du_skip(c, w)) {
+#pragma unroll
+            for (int q = 0; q < kClusterRowsPerThread; ++q) {
+                if (q >= nq) break;                       // uniform
+                const int r = my_r[q], cl = my_cl[q];
+                int g = 0;
+                long long uf = 0;
+                bool active = r >= 0;
+                if (active) {
+                    active = !w.cl_done[cl];
+                    if (active) {
+                        g = w.usage[r] - 1;
+                        const double ur = w.u[r];
+                        if (ur <= 0.0 && g < 0) g = 0;
+                        w.usage[r] = g;
+                        if (ur > 0.0) uf = to_fix(ur);
+                    }
+                }
+                warp_add_i(w.cl_nrm, cl, g * g, active);
+                warp_add_ll(w.cl_u, cl, uf, active);
+            }
+        }
+        cluster.sync();
+        du_decide_body(c, w);
+        cluster.sync();
+        // ---- apply the step (this thread's rows), per-tree reset, bookkeeping ----
+        if (c.idx && w.act_n[2]) {
+            if (gtid == 0) w.info[0] = 1;
+        } else {
+#pragma unroll
+            for (int q = 0; q < kClusterRowsPerThread; ++q) {
+                if (q >= nq) break;
+                const int r = my_r[q], cl = my_cl[q];
+                if (r < 0) continue;
+                const int fl = w.cl_flag[cl];
+                const double ur = w.u[r];
+                if (fl & 1) w.best_u[r] = ur;
+                if (!w.cl_done[cl]) w.u[r] = fmax(0.0, ur + w.cl_step[cl] * (double)w.usage[r]);
+                w.usage[r] = 0;
+            }
+            for (int t = gtid; t < c.n_trees; t += nth) {
+                w.cl_m[t] = 0;
+                w.cl_u[t] = 0;
+                w.cl_cost[t] = 0;
+                w.cl_nrm[t] = 0;
+                if (w.tstart[t] < 0) continue;
+                const int cl = w.uf[t];
+                if (w.cl_flag[cl] & 2) w.sel[t] = w.targ[t];
+                w.tdone[t] = w.cl_done[cl];
+                w.tmin[t] = kKeyInf;
+                w.targ[t] = -1;
+            }
+            if (gtid == 0) {
+                w.info[1] += 1;
+                w.stall_ctr[0] = w.stall_ctr[2] ? 0 : w.stall_ctr[0] + 1;
+                if (w.stall_ctr[1] == 0 || w.stall_ctr[0] >= kStallStop) w.info[0] = 1;
+                w.stall_ctr[1] = 0;
+                w.stall_ctr[2] = 0;
+            }
+        }
+        cluster.sync();
     }
 }
 
@@ -2138,11 +2320,83 @@ static int persistent_grid() {
     return blocks;
 }
 
+// cluster configuration the device can run: CTAs per cluster (16 non-portable, else 8, else 0 = no cluster
+// version) and the shared-memory slice capacity in columns
+struct ClusterPlan {
+    int ctas = 0, nc_cap = 0;
+    size_t smem = 0;
+};
+static ClusterPlan cluster_plan(int W) {
+    static ClusterPlan plans[MHT_MAX_WINDOW + 1];
+    static bool done[MHT_MAX_WINDOW + 1] = {false};
+    if (done[W]) return plans[W];
+    done[W] = true;
+    ClusterPlan best;
+    if (getenv("MHT_NO_CLUSTER_LOOP")) return plans[W] = best;
+    int dev = 0, optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const size_t budget = (size_t)optin - 2048;   // static shared memory of the greedy bodies + reserve
+    int nc_cap = (int)((budget - 64) / (8 + 8 + 4 + 4 * (size_t)W));
+    nc_cap &= ~31;
+    if (nc_cap < 256) return plans[W] = best;
+    const size_t smem = cluster_slice_bytes(nc_cap, W);
+    if (cudaFuncSetAttribute(dual_loop_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(dual_loop_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        return plans[W] = best;
+    }
+    for (int ctas : {kClusterCtas, 8}) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(ctas);
+        cfg.blockDim = dim3(kClusterThreads);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = ctas;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, dual_loop_cluster_kernel, &cfg) == cudaSuccess && n_clusters >= 1) {
+            best.ctas = ctas;
+            best.nc_cap = nc_cap;
+            best.smem = smem;
+            break;
+        }
+        cudaGetLastError();
+    }
+    return plans[W] = best;
+}
+
 static int dual_loop(const ColView &c, AssocWork &w, int iters, int grid_dim, cudaStream_t s) {
     ColView cc = c;
     AssocWork ww = w;
     static int greedy_every = getenv("MHT_GREEDY_EVERY") ? atoi(getenv("MHT_GREEDY_EVERY")) : kGreedyEvery;
-    void *args[] = {&cc, &ww, &iters, &greedy_every};
+    int *declined = w.act_n + 3;      // 0 = the cluster version ran the loop
+    const ClusterPlan plan = cluster_plan(c.width);
+    if (plan.ctas) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(plan.ctas);
+        cfg.blockDim = dim3(kClusterThreads);
+        cfg.dynamicSmemBytes = plan.smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = plan.ctas;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int nc_cap = plan.nc_cap;
+        count_launch();
+        MHT_CUDA(cudaLaunchKernelEx(&cfg, dual_loop_cluster_kernel, cc, ww, iters, greedy_every, nc_cap, declined));
+    } else {
+        static const int one = 1;
+        MHT_CUDA(cudaMemcpyAsync(declined, &one, sizeof(int), cudaMemcpyHostToDevice, s));
+    }
+    void *args[] = {&cc, &ww, &iters, &greedy_every, &declined};
     // grid.sync cost grows with the grid: the active list (~1e5 columns) gets one CTA per SM
     const int grid = grid_dim < persistent_grid() ? grid_dim : persistent_grid();
     count_launch();
