@@ -35,6 +35,10 @@ WORKLOADS = {
     # name: (targets, radarRange, lambda_phi, N, P_d, seed, maxNodes, maxParents)
     "cfg3_1k_targets_5k_meas_N6": (1000, 1142.0, 1e-3, 6, 0.9, 1234, 144 << 20, 32 << 20),
     "cfg2_100_targets_1k_meas_N4": (100, 1702.0, 1e-4, 4, 0.9, 1234, 1 << 22, 1 << 20),
+    # BASELINE config 4 (CV model; the coordinated-turn variant has no reference): 10x config 3.  Its forest
+    # peaks near 8e8 hypotheses per level while the window fills -- more than one GPU holds -- so it only runs tree
+    # sharded (--shard trees, 8 GPUs); the per-rank capacities below are the whole-region ones, divided by the ranks
+    "cfg4_10k_targets_50k_meas_N6": (10000, 3613.0, 1e-3, 6, 0.9, 1234, 1200 << 20, 280 << 20),
 }
 T_RADAR = 2.5
 
@@ -83,11 +87,17 @@ def make_scenario(name, n_scans, seed_offset=0):
     return simList, scans[:n_scans]
 
 
+def meas_capacity(name):
+    nT, R, lam = WORKLOADS[name][:3]
+    need = int(1.25 * (nT + lam * np.pi * R * R)) + 1024
+    return 8192 if need <= 8192 else 1 << int(np.ceil(np.log2(need)))
+
+
 def make_tracker(name):
     from pymht_b200.tracker import Tracker
     from pymht_b200.models import pv
     nT, R, lam, N, Pd, seed, max_nodes, max_par = WORKLOADS[name]
-    trk = Tracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=8192,
+    trk = Tracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=meas_capacity(name),
                   maxNodes=max_nodes, maxParents=max_par,
                   maxDualIterations=int(os.environ.get("MHT_DUAL_ITERS", "120")))
     trk.mergeThreshold = 0.0
@@ -256,6 +266,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     name = args.workload
     nT, R, lam, N, Pd, seed, _, _ = WORKLOADS[name]
+    if name.startswith("cfg4") and not (args.shard == "trees" and world > 1):
+        raise SystemExit("cfg4 (10k targets) exceeds one GPU's HBM while the window fills: run it with --shard trees "
+                         "under torchrun on 8 GPUs")
     config = {"workload": name, "targets": nT, "meas_per_scan": "~%d" % int(nT * Pd + lam * np.pi * R * R),
               "lambda_phi": lam, "n_scan": N, "P_d": Pd, "model": "CV (pv)", "radar_period_s": T_RADAR,
               "l2": "per-scan working set (hypothesis levels, GBs) exceeds the 126 MB L2; no explicit flush",
@@ -420,15 +433,43 @@ def main():
 
 
 def run_tree_sharded(args, name, config, dist, torch, rank, world, local_rank, preroll, n_scans):
-    """ONE region, its trees sharded over the ranks (pymht_b200/sharded.py): every rank gates its own trees, the
-    column records are all-gathered over NCCL, the global 0/1 program is solved on the gathered columns.  Timed
-    end to end through ShardedTracker.addMeasurementList (host scan in, tracks out), max over ranks."""
-    from pymht_b200.sharded import ShardedTracker
+    """ONE region, its trees sharded over the ranks (pymht_b200/sharded.py): every rank gates its own trees, ONE
+    all-gather of the packed column records (NCCL) gives every rank every column, the global 0/1 program is solved on
+    them (warm started; rank 0's selection is broadcast).  Timed end to end through ShardedTracker.addMeasurementList
+    (host scan in, tracks out), max over ranks.  Before the timed run the sharded tracker and a single forest (rank 0)
+    process the first scans of the scenario and their track digests are compared: parity where there is > 1 GPU."""
+    from pymht_b200.sharded import ShardedTracker, tracks_digest
+    from pymht_b200.tracker import Tracker
     from pymht_b200.models import pv
     nT, R, lam, N, Pd, seed, max_nodes, max_par = WORKLOADS[name]
     simList, scans = make_scenario(name, n_scans, seed_offset=0)      # the same region on every rank
+    dev = torch.device("cuda", local_rank)
+    mcap = meas_capacity(name)
+
+    # ---- parity leg: scans 1-2 (certified on both sides), sharded vs single forest ----
+    n_verify = 2
+    vt = ShardedTracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=mcap,
+                        maxNodes=1 << 22, maxParents=1 << 20, exactBudgetMs=10000)
+    vt.mergeThreshold = 0.0
+    vt.preInitialize(simList)
+    for s in scans[:n_verify]:
+        vt.addMeasurementList(s)
+    v_sharded = tracks_digest(vt.gatherTracks())
+    v_cert = [int(d["certified"]) for d in vt.scanInfo]
+    vt.close()
+    v_single = None
+    if rank == 0:
+        st = Tracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=mcap,
+                     maxNodes=1 << 22, maxParents=1 << 20, exactBudgetMs=10000)
+        st.mergeThreshold = 0.0
+        st.preInitialize(simList)
+        for s in scans[:n_verify]:
+            st.addMeasurementList(s)
+        v_single = tracks_digest([(n.ID, n.measurementNumber, n.cumulativeNLLR) for n in st.getTrackNodes()])
+        st.close()
+
     per = 1.0 / world + 0.15
-    trk = ShardedTracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=8192,
+    trk = ShardedTracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=mcap,
                          maxNodes=int(max_nodes * per), maxParents=int(max_par * per),
                          maxDualIterations=int(os.environ.get("MHT_DUAL_ITERS", "120")))
     trk.mergeThreshold = 0.0
@@ -441,16 +482,18 @@ def run_tree_sharded(args, name, config, dist, torch, rank, world, local_rank, p
         trk.addMeasurementList(s)
         times.append(time.perf_counter() - t0)
     timed = times[preroll + args.warmup:]
-    t = torch.tensor([sum(timed)], dtype=torch.float64, device=torch.device("cuda", local_rank))
+    t = torch.tensor([sum(timed)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     log = trk.exchangeLog[preroll + args.warmup:]
     infos = trk.scanInfo[preroll + args.warmup:]
-    n_tracks = len(trk.gatherTracks())
+    tracks = trk.gatherTracks()
+    n_tracks = len(tracks)
     if rank == 0:
         K = len(timed)
         v = K / float(t[0])
-        config = dict(config, parallelism="trees of one region sharded over %d GPUs; ragged all-gather of column "
-                      "records (NCCL) + replicated global solve" % world)
+        config = dict(config, scans=SCENARIO_SOURCE,
+                      parallelism="trees of one region sharded over %d GPUs; ONE all-gather of packed %d-byte column "
+                      "records per scan (NCCL) + replicated, warm-started global solve" % (world, log[-1]["record_bytes"]))
         line = {"metric": "scans/sec @ 1k targets, 5k meas/scan", "value": v, "unit": "scans/s", "n_gpus": world,
                 "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64 state / f32 covariance", "data": "synthetic", "config": config,
@@ -459,10 +502,18 @@ def run_tree_sharded(args, name, config, dist, torch, rank, world, local_rank, p
                 "stage_ms": {"ms_gate_rank0": float(np.mean([d["ms_gate"] for d in infos])),
                              "ms_exchange": float(np.mean([d["ms_exchange"] for d in log])),
                              "ms_solve": float(np.mean([d["ms_solve"] for d in log]))},
+                "scan_ms": {"p50": float(np.percentile(timed, 50) * 1e3), "p95": float(np.percentile(timed, 95) * 1e3),
+                            "max": float(np.max(timed) * 1e3)},
                 "exchange": {"columns_global": float(np.mean([d["n_cols_global"] for d in log])),
-                             "bytes_gathered_per_scan": float(np.mean([d["bytes_gathered"] for d in log]))},
-                "scan_stats": {"tracks": n_tracks, "objective": float(np.mean([d["objective"] for d in infos])),
-                               "lower_bound": float(np.mean([d["lower_bound"] for d in infos]))}}
+                             "bytes_gathered_per_scan": float(np.mean([d["bytes_gathered"] for d in log])),
+                             "collectives_per_scan": "1 all_gather_into_tensor of packed records (+ 16 B/rank of counts, "
+                                                     "the selection broadcast and the used-mask all-reduce)"},
+                "scan_stats": {"tracks": n_tracks, "tracks_hash": tracks_digest(tracks),
+                               "certified": float(np.mean([d["certified"] for d in infos])),
+                               "objective": float(np.mean([d["objective"] for d in infos])),
+                               "lower_bound": float(np.mean([d["lower_bound"] for d in infos]))},
+                "parity": {"scans": n_verify, "sharded_hash": v_sharded, "single_forest_hash": v_single,
+                           "equal": v_sharded == v_single, "certified": v_cert}}
         emit(line)
     trk.close()
     dist.destroy_process_group()

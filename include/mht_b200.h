@@ -110,6 +110,16 @@ int mht_assoc_solve(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t wid
                     const int32_t *d_col_tree, const int32_t *d_col_rows /* [width][n_cols] */,
                     int32_t *d_selected_col, double *h_info, void *d_work, void *stream);
 
+/* Same solve on persistent buffers: the column arrays have room for cap_cols columns (d_col_rows is [width][cap_cols])
+ * and d_work holds mht_assoc_workspace(cap_cols, n_trees, n_rows, width) bytes.  With warm != 0, d_work still holds the
+ * multipliers of the previous call with the SAME (cap_cols, n_trees, n_rows) and the solve starts from them; rows in
+ * [clear_row_lo, clear_row_hi) start from zero (the measurement plane being recycled for the new scan).  Used by the
+ * tree-sharded tracker, where measurement rows keep their ids for N+1 scans. */
+int mht_assoc_solve_warm(int64_t n_cols, int64_t cap_cols, int64_t n_trees, int64_t n_rows, int32_t width,
+                         const double *d_col_cost, const int32_t *d_col_tree, const int32_t *d_col_rows,
+                         int32_t *d_selected_col, double *h_info, void *d_work, void *stream, int32_t warm,
+                         int64_t clear_row_lo, int64_t clear_row_hi, double exact_ms /* <= 0: default 10 s */);
+
 /* ------------------------------------------------------------------------------------------------
  * Device-resident hypothesis forest: steps 1-3 + terminate + N-scan prune of
  * Tracker.addMeasurementList (tracker.py:194-259) with the forest kept in HBM across scans.
@@ -205,6 +215,15 @@ int mht_forest_grow(mht_forest *f, int64_t M, const double *z, int32_t z_on_devi
  * d_rows[w * stride + col_offset + j] = measurement row of path plane w (< 0: none), w < N+1. */
 int mht_forest_export_columns(mht_forest *f, int32_t tree_offset, int64_t col_offset, int64_t stride,
                               double *d_cost, int32_t *d_tree, int32_t *d_rows);
+/* The same columns as ONE packed record per column {f64 cost, i32 tree, i32 rows[N+1]} (mht_record_bytes(N+1)
+ * bytes each, 40 for N = 6): the payload of the single all-gather of SURVEY.md 8e.  mht_unpack_records turns the
+ * gathered buffer ([world][max_per_rank] records, rank r holding h_counts[r]) into the structure-of-arrays columns
+ * mht_assoc_solve takes, concatenated in rank order.  d_scratch: >= 1024 bytes of device memory. */
+int32_t mht_record_bytes(int32_t width);
+int mht_forest_export_records(mht_forest *f, int32_t tree_offset, void *d_records, int64_t cap_records);
+int mht_unpack_records(int32_t world, const int64_t *h_counts, int64_t max_per_rank, int32_t width,
+                       const void *d_gathered, int64_t stride_out, double *d_cost, int32_t *d_tree, int32_t *d_rows,
+                       void *d_scratch, void *stream);
 /* Close the open scan with an externally computed selection: d_selected_col[t] = LOCAL column index
  * (position in this forest's leaf order) for every tree slot t < n slots (ignored for dead slots).
  * h_assoc_info = the 8 doubles of mht_assoc_solve (may be NULL); fills info like mht_forest_scan. */

@@ -699,18 +699,34 @@ __global__ void __launch_bounds__(256) dual_loop_persistent_kernel(ColView c, As
 // Same arithmetic, same fixed-point sums: the result is bit-identical to the grid version.  The kernel declines
 // (info[kAssocInfo - 1] bit 30 stays clear -> the grid version runs) when the slice does not fit.
 // ------------------------------------------------------------------------------------------------
+__device__ unsigned long long g_loop_prof[16];   // ns per phase of the cluster loop (MHT_LOOP_PROF=1 prints them)
 constexpr int kClusterCtas = 16;
 constexpr int kClusterThreads = 1024;
 constexpr int kClusterRowsPerThread = 6;    // rows with a multiplier: <= 16 * 1024 * 6
+constexpr int kClusterTreesPerCta = 2048;   // span of tree ids one CTA's slice may cover
 
 __host__ __device__ inline size_t cluster_slice_bytes(int nc, int W) {
-    return (size_t)nc * (8 + 8 + 4 + 4 * (size_t)W) + 64;
+    return (size_t)nc * (8 + 8 + 4 + 4 * (size_t)W) + (size_t)kClusterTreesPerCta * 12 + 64;
+}
+
+// first position >= i of the iterated list where a new tree starts (columns are sorted by tree)
+__device__ __forceinline__ int tree_start_at_or_after(const ColView &c, int n, int i) {
+    if (i <= 0) return 0;
+    if (i >= n) return n;
+    int prev = c.tree[c.idx ? c.idx[i - 1] : i - 1];
+    while (i < n) {
+        const int t = c.tree[c.idx ? c.idx[i] : i];
+        if (t != prev) break;
+        ++i;
+    }
+    return i;
 }
 
 __global__ void __launch_bounds__(kClusterThreads, 1)
 dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, int nc_cap, int *declined) {
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char dl_smem[];
+    __shared__ int s_lo, s_hi;
     const int n = *c.n_ptr;
     const int nr = *w.row_n;
     const int nctas = (int)gridDim.x, nth = nctas * (int)blockDim.x;
@@ -721,12 +737,28 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
         if (gtid == 0) *declined = 1;
         return;
     }
+    // every CTA owns WHOLE trees: its slice starts at the first tree boundary at or after blockIdx * per, so the
+    // per-tree minimum / argmin never leave the CTA
+    if (threadIdx.x == 0) {
+        s_lo = tree_start_at_or_after(c, n, (int)blockIdx.x * per);
+        s_hi = blockIdx.x + 1 == gridDim.x ? n : tree_start_at_or_after(c, n, ((int)blockIdx.x + 1) * per);
+    }
     if (gtid == 0) *declined = 0;
-    const int lo = min(n, (int)blockIdx.x * per), hi = min(n, lo + per), nc = hi - lo;
+    __syncthreads();
+    const int lo = s_lo, hi = s_hi, nc = hi - lo;
+    const int t_first = nc > 0 ? c.tree[c.idx ? c.idx[lo] : lo] : 0;
+    const int t_last = nc > 0 ? c.tree[c.idx ? c.idx[hi - 1] : hi - 1] : -1;
+    const int ntl = t_last - t_first + 1;
+    cluster.sync();                                   // *declined = 0 is visible before anybody raises it
+    if (threadIdx.x == 0 && (nc > nc_cap || ntl > kClusterTreesPerCta)) atomicExch(declined, 1);
+    cluster.sync();
+    if (*(volatile int *)declined) return;            // uniform: the grid version takes over
     double *s_cost = (double *)dl_smem;
     double *s_rc = s_cost + nc_cap;
-    int *s_tree = (int *)(s_rc + nc_cap);
+    unsigned long long *s_tmin = (unsigned long long *)(s_rc + nc_cap);   // [kClusterTreesPerCta]
+    int *s_tree = (int *)(s_tmin + kClusterTreesPerCta);
     int *s_rows = s_tree + nc_cap;             // [W][nc_cap]
+    int *s_targ = s_rows + (size_t)c.width * nc_cap;                     // [kClusterTreesPerCta] local column of the argmin
     for (int k = threadIdx.x; k < nc; k += blockDim.x) {
         const int j = c.idx ? c.idx[lo + k] : lo + k;
         const int t = c.tree[j];
@@ -749,6 +781,15 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
     }
     __syncthreads();
     const int nc_round = (nc + 31) & ~31;
+    unsigned long long tp = 0;
+#define LOOP_PROF(slot)                                               \
+    if (gtid == 0) {                                                  \
+        unsigned long long now_;                                      \
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now_));      \
+        g_loop_prof[slot] += now_ - tp;                               \
+        tp = now_;                                                    \
+    }
+    if (gtid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tp));
     for (int it = 0; it < iters; ++it) {
         if (((volatile int *)w.info)[0]) break;  // uniform: written before the last cluster barrier
         if (it % greedy_every == 0) {
@@ -770,38 +811,72 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
                 if (blockIdx.x == 0) greedy_finish_body(c, w, w.tstart);
                 cluster.sync();
             }
+            LOOP_PROF(0)
         }
-        // ---- reduced costs + per-tree minimum: shared-memory slice, one hop to the multipliers ----
+        // ---- phase A, CTA local: reduced costs, per-tree minimum and argmin (ties -> last column) in shared memory,
+        //      then the tree's share of the subgradient: row usage, bound and cost sums ----
+        for (int tl = threadIdx.x; tl < ntl; tl += blockDim.x) {
+            // done flag of the tree (trees without columns in the slice never get looked at): one hop, all trees at once
+            s_tmin[tl] = w.tdone[t_first + tl] ? 0ull : kKeyInf;
+            s_targ[tl] = -1;
+        }
+        __syncthreads();
+        // pass 1: reduced costs -- nothing but loads and adds, so the gathers of a thread's columns overlap
+#pragma unroll 4
+        for (int k = threadIdx.x; k < nc; k += blockDim.x) {
+            double v = s_cost[k];
+            for (int q = 0; q < c.width; ++q) {
+                const int r = s_rows[q * nc_cap + k];
+                if (r >= 0) v += w.u[r];
+            }
+            s_rc[k] = v;
+        }
+        // pass 2: per-tree minimum (warp-aggregated over runs of equal tree); key 0 marks a finished tree
         for (int k = threadIdx.x; k < nc_round; k += blockDim.x) {
             int t = -1;
             unsigned long long key = kKeyInf;
             if (k < nc) {
                 t = s_tree[k];
-                if (!w.tdone[t]) {
-                    double v = s_cost[k];
-                    for (int q = 0; q < c.width; ++q) {
-                        const int r = s_rows[q * nc_cap + k];
-                        if (r >= 0) v += w.u[r];
-                    }
-                    s_rc[k] = v;
-                    key = f64_key(v);
-                } else {
-                    t = -1;
-                }
+                if (s_tmin[t - t_first] != 0ull) key = f64_key(s_rc[k]);
+                else t = -1;
             }
             const bool head = warp_run_min(t, key);
-            if (head && t >= 0) atomicMin(&w.tmin[t], key);
+            if (head && t >= 0) atomicMin(&s_tmin[t - t_first], key);
         }
-        cluster.sync();
-        // ---- argmin (ties -> last column) ----
+        __syncthreads();
         for (int k = threadIdx.x; k < nc; k += blockDim.x) {
-            const int t = s_tree[k];
-            if (w.tdone[t]) continue;
-            if (f64_key(s_rc[k]) == w.tmin[t]) atomicMax(&w.targ[t], c.idx ? c.idx[lo + k] : lo + k);
+            const int tl = s_tree[k] - t_first;
+            if (s_tmin[tl] != 0ull && f64_key(s_rc[k]) == s_tmin[tl]) atomicMax(&s_targ[tl], k);
+        }
+        __syncthreads();
+        LOOP_PROF(1)
+        if (!du_skip(c, w)) {
+            const int ntl_round = (ntl + 31) & ~31;
+            for (int tl = threadIdx.x; tl < ntl_round; tl += blockDim.x) {
+                const int k = tl < ntl ? s_targ[tl] : -1;
+                const bool active = k >= 0;
+                int cl = 0;
+                long long m = 0, cost = 0;
+                if (active) {
+                    const int t = t_first + tl;
+                    const int j = c.idx ? c.idx[lo + k] : lo + k;
+                    cl = w.uf[t];
+                    w.freq[j] += 1;  // ergodic primal estimate: how often this column is the tree's Lagrangian choice
+                    w.targ[t] = j;
+                    w.tmin[t] = s_tmin[tl];
+                    m = to_fix(key_f64(s_tmin[tl]));
+                    cost = to_fix(s_cost[k]);
+                    for (int q = 0; q < c.width; ++q) {
+                        const int r = s_rows[q * nc_cap + k];
+                        if (r >= 0) atomicAdd(&w.usage[r], 1);
+                    }
+                }
+                warp_add_ll(w.cl_m, cl, m, active);
+                warp_add_ll(w.cl_cost, cl, cost, active);
+            }
         }
         cluster.sync();
-        du_trees_body(c, w);
-        cluster.sync();
+        LOOP_PROF(3)
         // ---- rows: subgradient, norms (this thread's rows) ----
         if (!du_skip(c, w)) {
 #pragma unroll
@@ -826,8 +901,10 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
             }
         }
         cluster.sync();
+        LOOP_PROF(4)
         du_decide_body(c, w);
         cluster.sync();
+        LOOP_PROF(5)
         // ---- apply the step (this thread's rows), per-tree reset, bookkeeping ----
         if (c.idx && w.act_n[2]) {
             if (gtid == 0) w.info[0] = 1;
@@ -864,7 +941,10 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
             }
         }
         cluster.sync();
+        LOOP_PROF(6)
+        if (gtid == 0) g_loop_prof[7] += 1;
     }
+#undef LOOP_PROF
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2337,11 +2417,11 @@ static ClusterPlan cluster_plan(int W) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const size_t budget = (size_t)optin - 2048;   // static shared memory of the greedy bodies + reserve
-    int nc_cap = (int)((budget - 64) / (8 + 8 + 4 + 4 * (size_t)W));
+    int nc_cap = (int)((budget - 64 - (size_t)kClusterTreesPerCta * 12) / (8 + 8 + 4 + 4 * (size_t)W));
     nc_cap &= ~31;
     if (nc_cap < 256) return plans[W] = best;
     const size_t smem = cluster_slice_bytes(nc_cap, W);
-    if (cudaFuncSetAttribute(dual_loop_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+    if (cudaFuncSetAttribute(dual_loop_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess ||
         cudaFuncSetAttribute(dual_loop_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
         cudaGetLastError();
         return plans[W] = best;
@@ -2370,7 +2450,21 @@ static ClusterPlan cluster_plan(int W) {
     return plans[W] = best;
 }
 
+static void print_loop_prof() {
+    unsigned long long h[16];
+    if (cudaMemcpyFromSymbol(h, g_loop_prof, sizeof(h)) != cudaSuccess) return;
+    const double it = h[7] ? (double)h[7] : 1.0;
+    fprintf(stderr, "[mht] cluster loop, %.0f iterations: us/iteration greedy %.2f min+argmin %.2f trees %.2f rows %.2f "
+            "decide %.2f apply %.2f\n", it, h[0] / it * 1e-3, h[1] / it * 1e-3, h[3] / it * 1e-3, h[4] / it * 1e-3,
+            h[5] / it * 1e-3, h[6] / it * 1e-3);
+}
+
 static int dual_loop(const ColView &c, AssocWork &w, int iters, int grid_dim, cudaStream_t s) {
+    static bool prof_hook = false;
+    if (!prof_hook) {
+        prof_hook = true;
+        if (getenv("MHT_LOOP_PROF")) atexit(print_loop_prof);
+    }
     ColView cc = c;
     AssocWork ww = w;
     static int greedy_every = getenv("MHT_GREEDY_EVERY") ? atoi(getenv("MHT_GREEDY_EVERY")) : kGreedyEvery;
@@ -2547,7 +2641,12 @@ extern "C" int64_t mht_assoc_workspace(int64_t n_cols, int64_t n_trees, int64_t 
 
 static int make_view(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t width, const double *d_cost,
                      const int32_t *d_tree, const int32_t *d_rows, void *d_work, ColView *c, AssocWork *w,
-                     cudaStream_t s) {
+                     cudaStream_t s, int64_t cap_cols = -1) {
+    if (cap_cols < 0) cap_cols = n_cols;
+    if (cap_cols < n_cols) {
+        set_error("assoc: n_cols=%lld exceeds the column capacity %lld", (long long)n_cols, (long long)cap_cols);
+        return MHT_E_INVALID;
+    }
     if (n_cols < 0 || n_cols > 0x7ffffff0ll || n_trees <= 0 || n_trees >= (1 << 24) || n_rows < 0 ||
         n_rows > 0x7ffffff0ll || width < 0 || width > MHT_MAX_WINDOW || !d_work) {
         set_error("assoc: invalid argument (n_cols=%lld n_trees=%lld n_rows=%lld width=%d)", (long long)n_cols,
@@ -2557,7 +2656,7 @@ static int make_view(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t wi
     int *n_dev = (int *)d_work;
     const int n32 = (int)n_cols;
     MHT_CUDA(cudaMemcpyAsync(n_dev, &n32, sizeof(int), cudaMemcpyHostToDevice, s));
-    assoc_carve((char *)d_work + 256, n_cols, n_trees, n_rows, n_cols, w);
+    assoc_carve((char *)d_work + 256, cap_cols, n_trees, n_rows, cap_cols, w);
     c->n_ptr = n_dev;
     c->idx = nullptr;
     c->meas = nullptr;
@@ -2566,7 +2665,7 @@ static int make_view(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t wi
     c->tree_base = nullptr;
     c->tree = d_tree;
     c->rows = d_rows;
-    c->stride = n_cols;
+    c->stride = cap_cols;
     c->width = width;
     c->n_trees = (int)n_trees;
     c->n_rows = (int)(n_rows ? n_rows : 1);
@@ -2586,16 +2685,19 @@ extern "C" int mht_cluster(int64_t n_cols, int64_t n_trees, int64_t n_rows, int3
     return MHT_OK;
 }
 
-extern "C" int mht_assoc_solve(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t width,
-                               const double *d_col_cost, const int32_t *d_col_tree, const int32_t *d_col_rows,
-                               int32_t *d_selected_col, double *h_info, void *d_work, void *stream) {
+static int assoc_solve_entry(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t width, const double *d_col_cost,
+                             const int32_t *d_col_tree, const int32_t *d_col_rows, int32_t *d_selected_col, double *h_info,
+                             void *d_work, void *stream, bool warm, int64_t clear_lo, int64_t clear_hi,
+                             int64_t cap_cols = -1, double exact_ms = 10000.0) {
     if (int rc = check_device()) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     ColView c;
     AssocWork w;
-    if (int rc = make_view(n_cols, n_trees, n_rows, width, d_col_cost, d_col_tree, d_col_rows, d_work, &c, &w, s))
+    if (int rc = make_view(n_cols, n_trees, n_rows, width, d_col_cost, d_col_tree, d_col_rows, d_work, &c, &w, s, cap_cols))
         return rc;
-    if (int rc = assoc_solve(c, w, 200, 4096, kSMs * 4, s, nullptr, false, n_cols > 2000000, false, 10000.0)) return rc;
+    if (warm && clear_hi > clear_lo && clear_lo >= 0 && clear_hi <= n_rows)
+        MHT_CUDA(cudaMemsetAsync(w.u + clear_lo, 0, sizeof(double) * (size_t)(clear_hi - clear_lo), s));
+    if (int rc = assoc_solve(c, w, 200, 4096, kSMs * 4, s, nullptr, warm, n_cols > 2000000, false, exact_ms)) return rc;
     MHT_CUDA(cudaMemcpyAsync(d_selected_col, w.sel, n_trees * sizeof(int), cudaMemcpyDeviceToDevice, s));
     int info[kAssocInfo];
     double obj[2];
@@ -2619,4 +2721,20 @@ extern "C" int mht_assoc_solve(int64_t n_cols, int64_t n_trees, int64_t n_rows, 
         return MHT_E_NOTOPTIMAL;
     }
     return MHT_OK;
+}
+
+extern "C" int mht_assoc_solve(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t width,
+                               const double *d_col_cost, const int32_t *d_col_tree, const int32_t *d_col_rows,
+                               int32_t *d_selected_col, double *h_info, void *d_work, void *stream) {
+    return assoc_solve_entry(n_cols, n_trees, n_rows, width, d_col_cost, d_col_tree, d_col_rows, d_selected_col, h_info,
+                             d_work, stream, false, 0, 0);
+}
+
+extern "C" int mht_assoc_solve_warm(int64_t n_cols, int64_t cap_cols, int64_t n_trees, int64_t n_rows, int32_t width,
+                                    const double *d_col_cost, const int32_t *d_col_tree, const int32_t *d_col_rows,
+                                    int32_t *d_selected_col, double *h_info, void *d_work, void *stream, int32_t warm,
+                                    int64_t clear_row_lo, int64_t clear_row_hi, double exact_ms) {
+    return assoc_solve_entry(n_cols, n_trees, n_rows, width, d_col_cost, d_col_tree, d_col_rows, d_selected_col, h_info,
+                             d_work, stream, warm != 0, clear_row_lo, clear_row_hi, cap_cols,
+                             exact_ms > 0.0 ? exact_ms : 10000.0);
 }

@@ -1320,7 +1320,82 @@ __global__ void export_columns_kernel(Level cur, const int *rows_cur, long long 
     }
 }
 
+// packed column records for the multi-GPU exchange: {f64 cost, i32 tree, i32 rows[W]} padded to a multiple of 8 bytes
+__global__ void export_records_kernel(Level cur, const int *rows_cur, long long stride_in, int W, const int *d_nc,
+                                      const double *root_cnllr, int tree_offset, int rec_bytes, unsigned char *out) {
+    const int n = *d_nc;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int t = cur.tree[j];
+        unsigned char *rec = out + (size_t)j * rec_bytes;
+        *(double *)rec = cur.cnllr[j] - root_cnllr[t];
+        int *ri = (int *)(rec + 8);
+        ri[0] = t + tree_offset;
+        for (int w = 0; w < W; ++w) ri[1 + w] = rows_cur[w * stride_in + j];
+    }
+}
+
+// gathered records of every rank ([world][max_per_rank] records, rank r holds counts[r]) -> structure-of-arrays
+// columns at the global offsets (rank order = single-forest column order)
+__global__ void unpack_records_kernel(int world, const long long *counts, const long long *offsets, long long max_per_rank,
+                                      int W, int rec_bytes, const unsigned char *in, long long stride_out, double *cost,
+                                      int *tree, int *rows) {
+    for (int r = 0; r < world; ++r) {
+        const long long cnt = counts[r], off = offsets[r];
+        const unsigned char *base = in + (size_t)r * max_per_rank * rec_bytes;
+        for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < cnt; j += (long long)gridDim.x * blockDim.x) {
+            const unsigned char *rec = base + (size_t)j * rec_bytes;
+            cost[off + j] = *(const double *)rec;
+            const int *ri = (const int *)(rec + 8);
+            tree[off + j] = ri[0];
+            for (int w = 0; w < W; ++w) rows[w * stride_out + off + j] = ri[1 + w];
+        }
+    }
+}
+
 }  // namespace mht
+
+extern "C" int32_t mht_record_bytes(int32_t width) { return (12 + 4 * width + 7) / 8 * 8; }
+
+extern "C" int mht_forest_export_records(mht_forest *f, int32_t tree_offset, void *d_records, int64_t cap_records) {
+    if (!f || !d_records || cap_records < f->h_level_nodes_open()) {
+        set_error("mht_forest_export_records: invalid argument (need room for %lld records)",
+                  f ? (long long)f->h_level_nodes_open() : 0ll);
+        return MHT_E_INVALID;
+    }
+    if (f->T == 0) return MHT_OK;
+    count_launch(), export_records_kernel<<<kSMs * 8, 256, 0, f->stream>>>(
+        f->lv[f->scan % f->nslots], f->rows[f->scan & 1], f->cap_nodes, f->W, f->d_nc, f->ts.root_cnllr, tree_offset,
+        mht_record_bytes(f->W), (unsigned char *)d_records);
+    MHT_CUDA(cudaGetLastError());
+    MHT_CUDA(cudaStreamSynchronize(f->stream));
+    return MHT_OK;
+}
+
+extern "C" int mht_unpack_records(int32_t world, const int64_t *h_counts, int64_t max_per_rank, int32_t width,
+                                  const void *d_gathered, int64_t stride_out, double *d_cost, int32_t *d_tree,
+                                  int32_t *d_rows, void *d_scratch, void *stream) {
+    if (int rc = check_device()) return rc;
+    if (world < 1 || world > 64 || !h_counts || !d_gathered || !d_cost || !d_tree || !d_rows || !d_scratch) {
+        set_error("mht_unpack_records: invalid argument");
+        return MHT_E_INVALID;
+    }
+    long long host[128];
+    long long acc = 0;
+    for (int r = 0; r < world; ++r) {
+        host[r] = h_counts[r];
+        host[64 + r] = acc;
+        acc += h_counts[r];
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    MHT_CUDA(cudaMemcpyAsync(d_scratch, host, sizeof(host), cudaMemcpyHostToDevice, s));
+    count_launch(), unpack_records_kernel<<<kSMs * 8, 256, 0, s>>>(world, (const long long *)d_scratch,
+                                                                   (const long long *)d_scratch + 64, max_per_rank, width,
+                                                                   mht_record_bytes(width), (const unsigned char *)d_gathered,
+                                                                   stride_out, d_cost, d_tree, d_rows);
+    MHT_CUDA(cudaGetLastError());
+    MHT_CUDA(cudaStreamSynchronize(s));   // `host` is a stack buffer
+    return MHT_OK;
+}
 
 extern "C" int mht_forest_create(const mht_forest_config *cfg, mht_forest **out) {
     if (int rc = check_device()) return rc;

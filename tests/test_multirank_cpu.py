@@ -92,6 +92,55 @@ def test_tree_sharded_column_exchange_world2():
     assert r0[9] == [0, 2, -1, 4] and r1[9] == [0, -1, 2]       # global column -> local column
 
 
+def _pack_worker(rank, world, port, out):
+    """The ONE data-path collective of the tree-sharded tracker (padded packed records, all_gather_into_tensor) on gloo."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pymht_b200 import sharded as sh
+    W = 3
+    rec = np.dtype([("cost", "<f8"), ("tree", "<i4"), ("rows", "<i4", (W,))])      # 24 bytes = mht_record_bytes(3)
+    n_cols = [5, 3][rank]
+    cols, trees, col_off, tree_off = sh.exchange_counts(dist, torch, torch.device("cpu"), n_cols, [4, 3][rank])
+    mx = max(cols)
+    mine = np.zeros(mx, dtype=rec)
+    mine["cost"][:n_cols] = np.arange(n_cols) + 100 * rank
+    mine["tree"][:n_cols] = tree_off[rank] + np.arange(n_cols) % [4, 3][rank]
+    mine["rows"][:n_cols] = 1000 * rank + np.arange(n_cols)[:, None] * 10 + np.arange(W)[None, :]
+    send = torch.from_numpy(mine.view(np.uint8).copy())
+    gathered = torch.empty(world * mx * rec.itemsize, dtype=torch.uint8)
+    sh.pack_exchange(dist, torch, send, gathered)
+    g = gathered.numpy().view(rec).reshape(world, mx)
+    flat = np.concatenate([g[r, :cols[r]] for r in range(world)])                  # rank order = single-forest order
+    out.put((rank, rec.itemsize, flat["cost"].tolist(), flat["tree"].tolist(), flat["rows"].tolist()))
+    dist.destroy_process_group()
+
+
+def test_packed_record_all_gather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 32500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_pack_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    r0, r1 = res
+    assert r0[1] == 24
+    assert r0[2] == r1[2] == [0, 1, 2, 3, 4, 100, 101, 102]
+    assert r0[3] == r1[3] == [0, 1, 2, 3, 0, 4, 5, 6]
+    assert r0[4] == r1[4] and r0[4][5] == [1000, 1001, 1002]
+
+
+def test_tracks_digest_is_order_independent():
+    from pymht_b200 import sharded as sh
+    a = [(3, 7, -1.25, None), (1, 0, 2.0, None)]
+    assert sh.tracks_digest(a) == sh.tracks_digest(a[::-1])
+    assert sh.tracks_digest(a) != sh.tracks_digest([(3, 7, -1.25, None), (1, 1, 2.0, None)])
+
+
 def test_shard_bounds_cover_everything():
     from pymht_b200 import sharded as sh
     for n in (0, 1, 7, 1000):
