@@ -230,6 +230,15 @@ int mht_unpack_records(int32_t world, const int64_t *h_counts, int64_t max_per_r
 int mht_forest_select(mht_forest *f, const int32_t *d_selected_col, const double *h_assoc_info,
                       mht_scan_info *info);
 
+/* Tracker.__dynamicWindow (tracker.py:918-950).  enabled: apply the SIZE criterion on the device in every following
+ * scan -- a tree holding more than target_size_limit nodes after the scan's growth (Target.getNumOfNodes,
+ * pyTarget.py:148-151; tracker.py:118 default 3000) loses one scan of its N-scan window before the scan's pruning.
+ * window_roof (0 = N): upper limit for every tree's window, what the reference lowers when a whole iteration
+ * exceeds 0.8 x radarPeriod (tracker.py:943-950); the wall-clock criteria themselves stay with the host, which
+ * owns the clock.  mht_forest_windows reads the per-tree windows back (__targetWindowSize__, tracker.py:83). */
+int mht_forest_set_dynamic_window(mht_forest *f, int32_t enabled, int32_t target_size_limit, int32_t window_roof);
+int mht_forest_windows(mht_forest *f, int32_t cap, int32_t *n, int32_t *h_slot, int32_t *h_window);
+
 /* Selected hypothesis per live tree after the last scan (Tracker.getTrackNodes, tracker.py:976):
  * h_slot[T] tree slot, h_x[T,4], h_P[T,16], h_cnllr[T], h_meas[T] (measurementNumber, 0 = miss),
  * h_status[T] (0 active, 1 out-of-range, 2 too-low-score; dead tracks are reported once, in the scan

@@ -38,6 +38,11 @@ def _scenario(name):
         # 1000 targets in the config-3 scene with 10x less clutter: 3 scans are what the reference
         # finishes in minutes (2.5 s, 5.6 s, 330 s); 140 + 140 + 32 multi-tree ILPs
         return None, 3, 1142.0, 1e-4, 6, 0.9, 4321, 1000
+    if name == "cfg2_dynwin":
+        # cfg2_small's scene with addMeasurementList(dynamicWindow=True) and a small targetSizeLimit so that the
+        # size criterion of Tracker.__dynamicWindow (tracker.py:918-950) fires; the wall-clock criteria are disabled
+        # (limits set out of reach) because they depend on the host's speed
+        return None, 12, 760.0, 2e-4, 4, 0.9, 4242, 20
     if name == "cfg3_scan3":
         return None, 3, 1142.0, 1e-3, 6, 0.9, 1234, 1000
     if name == "cfg5_small":
@@ -93,13 +98,19 @@ def run_reference(name):
     scans = sim.simulateScans(simList, T_RADAR, pv.C_RADAR, pv.R_RADAR(pv.sigmaR_RADAR_true), lam, R, p0,
                               shuffle=True, localClutter=False, globalClutter=True, preInitialized=True)
     trk = ref_shim.make_reference_tracker(T_RADAR, lam, 1e-9, N=N, P_d=Pd)
+    scan_kw = {}
+    if name == "cfg2_dynwin":
+        trk.targetSizeLimit = 60
+        trk.totalGrowTimeLimit = trk.nodeGrowTimeLimit = 1e9
+        trk.radarPeriod = 1e9            # only read by the window-roof test of __dynamicWindow (0.8 * radarPeriod)
+        scan_kw = {"dynamicWindow": True}
     trk.preInitialize(simList)
     out = {"init_x": np.array([t.cartesianState() for t in simList[0]], dtype=np.float64),
            "init_time": np.float64(T0), "n_scans": np.int64(len(scans)),
            "params": np.array([T_RADAR, lam, 1e-9, N, Pd, 5.99, R])}
     for k, scan in enumerate(scans):
         t = time.time()
-        trk.addMeasurementList(scan)
+        trk.addMeasurementList(scan, **scan_kw)
         wall = time.time() - t
         nodes = list(trk.getTrackNodes())
         hist = hpf.backtrackMeasurementNumbers(nodes)
@@ -119,6 +130,7 @@ def run_reference(name):
         out[pre + "nclusters"] = np.int64(len(trk.__clusterList__))
         out[pre + "n_ilp"] = np.int64(trk.nOptimSolved)
         out[pre + "toc"] = np.array([trk.toc[s] for s in ("Process", "Cluster", "Optim", "Terminate", "N-Prune")])
+        out[pre + "window"] = np.array(trk.__targetWindowSize__, dtype=np.int64)
         print("%s scan %d: M=%d tracks=%d leaves=%d clusters=%d ilps=%d wall=%.2fs" % (
             name, k + 1, len(scan.measurements), len(nodes), int(out[pre + "nleaves"].sum()),
             len(trk.__clusterList__), trk.nOptimSolved, wall), flush=True)

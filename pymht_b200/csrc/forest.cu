@@ -121,6 +121,9 @@ struct mht_forest {
     int64_t h_level_nodes;     // nodes in the current level (for initiate)
     std::vector<int> last_tracks;  // tree slots reported by the last scan
     bool open_scan = false;        // mht_forest_grow done, mht_forest_select pending
+    // dynamic window (Tracker.__dynamicWindow, tracker.py:918-950): size criterion on device, roof from the host
+    int dyn_window = 0, target_size_limit = 3000, window_roof = 0;
+    double *adv_d = nullptr, *adv_h = nullptr;   // [T][kMaxAdv - 1][kHistRec] nodes a root skipped over in one scan
     int64_t open_M = 0, open_children = 0;
     int64_t h_level_nodes_open() const { return open_children; }
 };
@@ -733,6 +736,9 @@ __global__ void tree_off_kernel(ScanArgs a) {
     }
 }
 
+constexpr int kMaxAdv = 4;      // levels a root may advance in one scan (N-scan pruning: 1; dynamic window: up to 3)
+constexpr int kAdvRec = 24;     // = kHistRec: meas, cnllr, x[4], scan, pad, P[16]
+
 struct UpdateArgs {
     Level lv[MHT_MAX_WINDOW + 2];
     int nslots, W, T, scan, N;
@@ -748,6 +754,8 @@ struct UpdateArgs {
     const int *row_n;
     mht_model model;
     double score_upper, cnllr_upper, radar_range, px, py;
+    int dyn_window, target_size_limit, window_roof;
+    double *adv;            // [T][kMaxAdv - 1][kHistRec]
 };
 
 __device__ __forceinline__ int path_cmp(const UpdateArgs &a, int p, int q, int s_lo, int s_hi) {
@@ -790,6 +798,22 @@ __global__ void track_update_kernel(UpdateArgs a) {
     a.out.cnllr[t] = cn;
     for (int i = 0; i < 4; ++i) a.out.x[4 * t + i] = x[i];
     const int root_old = a.ts.root_scan[t];
+    if (a.dyn_window) {
+        // Tracker.__dynamicWindow (tracker.py:918-950), size criterion: a tree of more than targetSizeLimit nodes
+        // (Target.getNumOfNodes, pyTarget.py:148-151: the root and everything below it, after this scan's growth)
+        // loses one scan of window.  The surviving nodes of every level are the contiguous range between the
+        // ancestors of the first and the last leaf.
+        long long size = 1;
+        int lo_p = cur.tree_off[t], hi_p = cur.tree_off[t + 1] - 1;
+        for (int s2 = a.scan; s2 > root_old && hi_p >= lo_p; --s2) {
+            size += hi_p - lo_p + 1;
+            const Level &L = a.lv[s2 % a.nslots];
+            lo_p = L.par_lo[t] + (L.pidx[lo_p] - L.par_off[t]);
+            hi_p = L.par_lo[t] + (L.pidx[hi_p] - L.par_off[t]);
+        }
+        if (size > a.target_size_limit) a.ts.window[t] -= 1;
+    }
+    if (a.ts.window[t] > a.window_roof) a.ts.window[t] = a.window_roof;   // roof lowered by the host (tracker.py:943-950)
     const unsigned pat_sel = cur.pat[sel];
     const int depth_sel = min(a.scan - root_old, 16);
     const double Pd_t = a.ts.Pd[t];
@@ -811,7 +835,9 @@ __global__ void track_update_kernel(UpdateArgs a) {
         atomicAdd(&a.status->n_dead, 1);
         return;
     }
-    const int root_new = max(root_old, a.scan - a.ts.window[t]);
+    // Target.pruneDepth (pyTarget.py:343-356): the new root is window[t] scans above the selected leaf (the leaf
+    // itself once the window is <= 0), never above the current root
+    const int root_new = min(a.scan, max(root_old, a.scan - a.ts.window[t]));
     int lo = cur.tree_off[t], hi = cur.tree_off[t + 1];
     if (root_new > root_old) {
         // walk up from the selected leaf to the new root
@@ -821,6 +847,28 @@ __global__ void track_update_kernel(UpdateArgs a) {
             pos = L.par_lo[t] + (L.pidx[pos] - L.par_off[t]);
         }
         const Level &LR = a.lv[root_new % a.nslots];
+        // nodes the root skips over when it advances more than one level (dynamic window): the host keeps them in
+        // the track's trunk, oldest first at slot 0
+        if (root_new - root_old > 1 && a.adv) {
+            int p2 = pos;
+            for (int s2 = root_new; s2 > root_old + 1; --s2) {
+                const Level &L2 = a.lv[s2 % a.nslots];
+                p2 = L2.par_lo[t] + (L2.pidx[p2] - L2.par_off[t]);
+                const int lvl = s2 - 1;                       // p2 is the node of scan lvl
+                const int slot = lvl - (root_old + 1);
+                if (slot >= kMaxAdv - 1) continue;
+                const Level &L3 = a.lv[lvl % a.nslots];
+                double *o = a.adv + ((size_t)t * (kMaxAdv - 1) + slot) * kAdvRec;
+                float Pn[16];
+                chain_P(a.model, a.ts.rootP + 16 * t, pat_sel >> (depth_sel - (lvl - root_old)), lvl - root_old, Pd_t, Pn);
+                o[0] = (double)L3.meas[p2];
+                o[1] = L3.cnllr[p2];
+                const double2 q01 = L3.xa[p2], q23 = L3.xb[p2];
+                o[2] = q01.x; o[3] = q01.y; o[4] = q23.x; o[5] = q23.y;
+                o[6] = (double)lvl;
+                for (int i = 0; i < 16; ++i) o[8 + i] = (double)Pn[i];
+            }
+        }
         a.ts.root_cnllr[t] = LR.cnllr[pos];
         a.ts.root_scan[t] = root_new;
         a.out.advanced[t] = root_new - root_old;
@@ -993,6 +1041,7 @@ static int forest_layout(mht_forest *f, bool commit) {
     f->hist_d = carve<double>(p, kHistRec * (MHT_MAX_WINDOW + 4));
     f->histb_d = carve<double>(p, (int64_t)256 * kHistRec * (MHT_MAX_WINDOW + 4));
     f->dead_d = carve<int>(p, 2 * 256);
+    f->adv_d = carve<double>(p, (int64_t)T * (kMaxAdv - 1) * kAdvRec);
     const int64_t n_rows = (int64_t)f->W * f->cfg.max_meas;
     const int64_t cap_cand = cn < (int64_t)T * 256 ? cn : (int64_t)T * 256;
     f->assoc_ws = p;
@@ -1025,6 +1074,10 @@ static void fill_update_args(mht_forest *f, UpdateArgs *u) {
     u->radar_range = f->cfg.radar_range;
     u->px = f->cfg.position[0];
     u->py = f->cfg.position[1];
+    u->dyn_window = f->dyn_window;
+    u->target_size_limit = f->target_size_limit;
+    u->window_roof = f->window_roof > 0 ? f->window_roof : f->cfg.n_scan_window;
+    u->adv = f->adv_d;
 }
 
 // phase: 0 = whole scan; 1 = grow only (gate stage; the caller exchanges columns and calls the finish
@@ -1195,6 +1248,9 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     MHT_CUDA(cudaMemcpyAsync(f->out_h_base, f->out_d_base, (size_t)f->out_bytes, cudaMemcpyDeviceToHost, s));
     MHT_CUDA(cudaMemcpyAsync(f->status_h, f->status_d, sizeof(ScanStatus), cudaMemcpyDeviceToHost, s));
     if (h_used) MHT_CUDA(cudaMemcpyAsync(f->used_h, f->used_d, (size_t)M, cudaMemcpyDeviceToHost, s));
+    if (f->dyn_window)   // roots may have advanced several levels: the nodes they skipped
+        MHT_CUDA(cudaMemcpyAsync(f->adv_h, f->adv_d, sizeof(double) * (size_t)f->T * (kMaxAdv - 1) * kAdvRec,
+                                 cudaMemcpyDeviceToHost, s));
     MHT_CUDA(cudaEventRecord(f->ev[4], s));
     MHT_CUDA(cudaStreamSynchronize(s));
     if (h_used && M) memcpy(h_used, f->used_h, (size_t)M);
@@ -1222,6 +1278,16 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
         }
         if (f->out_h.advanced[t] > 0) {
             TrunkNode nd;
+            for (int k = 0; k + 1 < f->out_h.advanced[t] && k < kMaxAdv - 1 && f->dyn_window; ++k) {
+                const double *o = f->adv_h + ((size_t)t * (kMaxAdv - 1) + k) * kAdvRec;
+                TrunkNode mid;
+                mid.scan = (int)o[6];
+                mid.meas = (int)o[0];
+                mid.cnllr = o[1];
+                memcpy(mid.x, o + 2, sizeof(mid.x));
+                for (int q = 0; q < 16; ++q) mid.P[q] = (float)o[8 + q];
+                f->trunk[t].push_back(mid);
+            }
             f->h_root_scan[t] += f->out_h.advanced[t];
             nd.scan = f->h_root_scan[t];
             nd.meas = f->out_h.root_meas[t];
@@ -1433,6 +1499,7 @@ extern "C" int mht_forest_create(const mht_forest_config *cfg, mht_forest **out)
     if (e == cudaSuccess) e = cudaMallocHost(&f->hist_h, kHistRec * sizeof(double) * (MHT_MAX_WINDOW + 4));
     if (e == cudaSuccess) e = cudaMallocHost(&f->histb_h, sizeof(double) * 256 * kHistRec * (MHT_MAX_WINDOW + 4));
     if (e == cudaSuccess) e = cudaMallocHost(&f->dead_h, sizeof(int) * 2 * 256);
+    if (e == cudaSuccess) e = cudaMallocHost(&f->adv_h, sizeof(double) * (size_t)cfg->max_trees * (kMaxAdv - 1) * kAdvRec);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&f->ev[i]);
     for (int i = 0; i < 10 && e == cudaSuccess; ++i) e = cudaEventCreate(&f->evx[i]);
@@ -1477,6 +1544,7 @@ extern "C" void mht_forest_destroy(mht_forest *f) {
     cudaFreeHost(f->hist_h);
     cudaFreeHost(f->histb_h);
     cudaFreeHost(f->dead_h);
+    cudaFreeHost(f->adv_h);
     cudaFree(f->arena);
     delete f;
 }
@@ -1651,6 +1719,45 @@ extern "C" int mht_forest_min_leaf_distance(mht_forest *f, double px, double py,
     } else {
         unsigned long long u = (h & 0x8000000000000000ull) ? (h & 0x7fffffffffffffffull) : ~h;
         memcpy(dist, &u, 8);
+    }
+    return MHT_OK;
+}
+
+extern "C" int mht_forest_set_dynamic_window(mht_forest *f, int32_t enabled, int32_t target_size_limit,
+                                             int32_t window_roof) {
+    if (!f || target_size_limit < 1 || window_roof < 0 || window_roof > f->cfg.n_scan_window) {
+        set_error("mht_forest_set_dynamic_window: invalid argument");
+        return MHT_E_INVALID;
+    }
+    f->dyn_window = enabled ? 1 : 0;
+    f->target_size_limit = target_size_limit;
+    f->window_roof = window_roof;
+    return MHT_OK;
+}
+
+extern "C" int mht_forest_windows(mht_forest *f, int32_t cap, int32_t *n, int32_t *h_slot, int32_t *h_window) {
+    if (!f || !n || !h_slot || !h_window) {
+        set_error("mht_forest_windows: invalid argument");
+        return MHT_E_INVALID;
+    }
+    std::vector<int> win(f->T > 0 ? f->T : 1);
+    if (f->T > 0) {
+        MHT_CUDA(cudaMemcpyAsync(win.data(), f->ts.window, sizeof(int) * (size_t)f->T, cudaMemcpyDeviceToHost, f->stream));
+        MHT_CUDA(cudaStreamSynchronize(f->stream));
+    }
+    int k = 0;
+    for (int t = 0; t < f->T; ++t) {
+        if (!f->h_alive[t]) continue;
+        if (k < cap) {
+            h_slot[k] = t;
+            h_window[k] = win[t];
+        }
+        ++k;
+    }
+    *n = k;
+    if (k > cap) {
+        set_error("mht_forest_windows: %d live trees exceed cap %d", k, cap);
+        return MHT_E_CAPACITY;
     }
     return MHT_OK;
 }

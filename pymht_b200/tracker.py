@@ -71,6 +71,10 @@ class Tracker:
         self.clnnrUpperLimit = 3.0
         if kwargs.get("pruneSimilar", False):
             raise NotImplementedError("pruneSimilar is outside the accelerated path")
+        self.targetSizeLimit = 3000                                  # tracker.py:118
+        self.totalGrowTimeLimit = self.radarPeriod * 0.5             # tracker.py:47
+        self.nodeGrowTimeLimit = 200e-3                              # tracker.py:48
+        self._dynWindowOn = False
 
         # device forest capacities (HBM): hypotheses per level / live leaves per scan
         self.maxTargets = int(kwargs.get("maxTargets", 4096))
@@ -156,9 +160,14 @@ class Tracker:
     def addMeasurementList(self, scanList, aisList=None, **kwargs):
         if aisList is not None and len(aisList) > 0:
             raise NotImplementedError("AIS fusion (tracker.py:417-552) is outside the accelerated path")
-        for kw in ("dynamicWindow", "pruneSimilar"):
-            if kwargs.get(kw, False):
-                raise NotImplementedError(kw + " is outside the accelerated path")
+        if kwargs.get("pruneSimilar", False):
+            raise NotImplementedError("pruneSimilar is outside the accelerated path")
+        dyn = bool(kwargs.get("dynamicWindow", False))
+        if dyn or self._dynWindowOn:
+            # tracker.py:244-248,918-950: the size criterion runs on the device inside this scan, before its pruning
+            _lib.check(self._lib.mht_forest_set_dynamic_window(self._forest, int(dyn), int(self.targetSizeLimit),
+                                                               int(self.N) if self.N < self.N_max else 0))
+            self._dynWindowOn = dyn
         self.tic.clear()
         self.toc.clear()
         t_total = time.time()
@@ -187,7 +196,10 @@ class Tracker:
         self.toc["Cluster"] = info.ms_cluster * 1e-3
         self.toc["Optim"] = info.ms_assoc * 1e-3
         self.toc["ILP-Prune"] = 0.0
-        self.toc["DynN"] = 0.0
+        t_dyn = time.time()
+        if dyn:
+            self._read_windows()
+        self.toc["DynN"] = time.time() - t_dyn
         t_term = time.time()
         self._collect_tracks(scanList)
         self.toc["Terminate"] = time.time() - t_term
@@ -199,6 +211,16 @@ class Tracker:
             self.initiateTarget(initial_target)
         self.toc["Init"] = time.time() - t_init
         self.toc["Total"] = time.time() - t_total
+        if dyn:
+            # wall-clock part of __dynamicWindow (tracker.py:919-925,943-950): all trees grow in ONE batched device
+            # pass, so a tree's share of the grow time is its share of the leaves; the roof on N follows the
+            # reference's 0.8 x radarPeriod test.  Both act on the NEXT scan's pruning (the reference applies them
+            # inside the same scan; its per-target clocks do not exist here).
+            if info.ms_gate * 1e-3 > self.totalGrowTimeLimit or self.toc["Total"] > self.radarPeriod * 0.8:
+                self.N = max(1, self.N - 1)
+                log.warning("Iteration took too long (%.1f ms), reducing window size roof from %d to %d",
+                            1e3 * self.toc["Total"], self.N + 1, self.N)
+                self.__targetWindowSize__ = [min(e, self.N) for e in self.__targetWindowSize__]
         for k, v in self.runtimeLog.items():
             if k in self.toc:
                 v.append(self.toc[k])
@@ -240,6 +262,16 @@ class Tracker:
         else:
             self._live_rows = None
         self.__trackNodes__ = None       # built on demand
+
+    def _read_windows(self):
+        """__targetWindowSize__ (tracker.py:83) after the device applied the size criterion of this scan."""
+        cap = max(len(self._slots), 1)
+        n = C.c_int32()
+        slot = np.zeros(cap, dtype=np.int32)
+        win = np.zeros(cap, dtype=np.int32)
+        _lib.check(self._lib.mht_forest_windows(self._forest, cap, C.byref(n), _lib.ptr(slot), _lib.ptr(win)))
+        by_slot = dict(zip(slot[:n.value].tolist(), win[:n.value].tolist()))
+        self.__targetWindowSize__ = [by_slot.get(s, w) for s, w in zip(self._slots, self.__targetWindowSize__)]
 
     def _make_node(self, row, slot, dead=False):
         scanList, scanNumber, x, P, cn, meas, status = self._last
