@@ -38,6 +38,25 @@ def _scenario(name):
         # 1000 targets in the config-3 scene with 10x less clutter: 3 scans are what the reference
         # finishes in minutes (2.5 s, 5.6 s, 330 s); 140 + 140 + 32 multi-tree ILPs
         return None, 3, 1142.0, 1e-4, 6, 0.9, 4321, 1000
+    if name == "cfg5_full":
+        # BASELINE config 5 at full size: 500 targets = 50 pairs scripted to cross at 90 degrees on
+        # the SAME scan (scan 5), less than one gate radius apart for +-2 scans, plus 400 background targets;
+        # lambda = 1e-4, R = 1702 m, N = 8, seed 77
+        rng5 = np.random.RandomState(77)
+        xs = []
+        for k in range(50):
+            c = rng5.uniform(-1100, 1100, size=2)
+            v = 4.0                               # 10 m per scan: within the 19.5 m gate radius for scans 3..7
+            tc = 5 * T_RADAR
+            xs.append([c[0] - v * tc, c[1] + 2.0, v, 0.0])
+            xs.append([c[0] + 2.0, c[1] - v * tc, 0.0, v])
+        for k in range(400):
+            r = 1300.0 * np.sqrt(rng5.uniform())
+            th = rng5.uniform(0, 2 * np.pi)
+            a = rng5.uniform(0, 2 * np.pi)
+            sp = rng5.choice([0.5, 5.0, 6.0, 7.5])
+            xs.append([r * np.cos(th), r * np.sin(th), sp * np.cos(a), sp * np.sin(a)])
+        return np.array(xs), 6, 1702.0, 1e-4, 8, 0.9, 77      # scan 7 (2e5 leaves, one cluster) is out of the reference's reach
     if name == "cfg2_dynwin":
         # cfg2_small's scene with addMeasurementList(dynamicWindow=True) and a small targetSizeLimit so that the
         # size criterion of Tracker.__dynamicWindow (tracker.py:918-950) fires; the wall-clock criteria are disabled

@@ -280,7 +280,7 @@ class Tracker:
         return Target(scanList.time, scanNumber, x[row].copy(), P[row].copy(), ID=root.ID, P_d=root.P_d,
                       measurementNumber=m, measurement=(np.asarray(scanList.measurements)[m - 1] if m > 0 else None),
                       cumulativeNLLR=float(cn[row]), status=STATUS_TAGS[int(status[row])],
-                      parent_loader=self._make_parent_loader(slot, dead))
+                      parent_loader=self._make_parent_loader(slot, dead, self._window_of(slot)))
 
     def _history(self, slot):
         cap = 64
@@ -299,8 +299,15 @@ class Tracker:
             k = n.value
             return meas[:k], x[:k], cn[:k], P[:k]
 
-    def _make_parent_loader(self, slot, dead=False):
+    def _window_of(self, slot):
+        try:
+            return int(self.__targetWindowSize__[self._slots.index(slot)])
+        except ValueError:      # the track died this scan: it was not pruned
+            return self.N
+
+    def _make_parent_loader(self, slot, dead=False, window=None):
         scan_at_creation = len(self.__scanHistory__)
+        window = self.N if window is None else max(0, window)
 
         def load(leaf):
             if not dead and len(self.__scanHistory__) != scan_at_creation:
@@ -312,7 +319,7 @@ class Tracker:
             # current root of the tree: N scans above the leaf once the window is full (tracker.py:1219-1231);
             # a track terminated this scan was not pruned, its root is one scan older
             pruned_at = leaf.scanNumber - (0 if leaf.status == STATUS_TAGS[0] else 1)
-            root_scan = max(first_scan, pruned_at - self.N)
+            root_scan = max(first_scan, pruned_at - window)
             chain = Target(root.time, first_scan, x[0].copy(), P[0].copy(), ID=root.ID, P_d=root.P_d,
                            status=root.status, cumulativeNLLR=float(cn[0]), isRoot=(root_scan == first_scan))
             for k in range(1, len(meas) - 1):

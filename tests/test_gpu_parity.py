@@ -154,7 +154,7 @@ def test_cluster_and_assoc_vs_oracle(name, upto):
         assert len(used) == len(set(used.tolist()))
 
 
-def _replay_tracker(name, n_scans=None, **kw):
+def _replay_tracker(name, n_scans=None, scan_kw=None, setup=None, **kw):
     from pymht_b200.tracker import Tracker, backtrackMeasurementNumbers
     from pymht_b200.models import pv
     from pymht_b200.pyTarget import Target
@@ -163,12 +163,14 @@ def _replay_tracker(name, n_scans=None, **kw):
     T, lam_phi, lam_nu, N, Pd, eta2, R = [float(v) for v in g["params"]]
     trk = Tracker(pv, T, lam_phi, lam_nu, eta2=eta2, N=int(N), P_d=Pd, **kw)
     trk.mergeThreshold = 0.0
+    if setup:
+        setup(trk)
     for x in g["init_x"]:
         trk.initiateTarget(Target(float(g["init_time"]), None, x, pv.P0, status="preinitialized"))
     stats = []
     for k in range(int(g["n_scans"]) if n_scans is None else n_scans):
         pre = "s%d_" % k
-        trk.addMeasurementList(MeasurementList(float(g[pre + "time"]), g[pre + "z"]))
+        trk.addMeasurementList(MeasurementList(float(g[pre + "time"]), g[pre + "z"]), **(scan_kw or {}))
         nodes = list(trk.getTrackNodes())
         info = trk.scanInfo[-1]
         stats.append(info)
@@ -195,6 +197,29 @@ def test_tracker_replays_reference_golden(name):
         assert info["n_clusters"] == int(g[pre + "nclusters"])
         assert info["n_multi_clusters"] == int(g[pre + "n_ilp"])
         trk._checkTrackerIntegrity()
+
+
+def test_dynamic_window_matches_reference():
+    """addMeasurementList(dynamicWindow=True) (tracker.py:244-248,918-950): the reference ran this fixture with
+    targetSizeLimit = 60 and its wall-clock criteria out of reach, so only the size criterion fires -- per-tree windows
+    shrink 4 -> 3 -> 2, roots advance several levels in one scan.  Windows, tracks, histories and leaf counts must
+    follow the reference scan by scan."""
+    def setup(trk):
+        trk.targetSizeLimit = 60
+        trk.totalGrowTimeLimit = trk.nodeGrowTimeLimit = 1e9
+        trk.radarPeriod = 1e9
+    for k, g, pre, trk, nodes, hist, info in _replay_tracker("cfg2_dynwin", scan_kw={"dynamicWindow": True}, setup=setup):
+        assert info["certified"] == 1, (k, info)
+        assert [n.ID for n in nodes] == list(g[pre + "ids"]), k
+        assert list(trk.__targetWindowSize__) == list(g[pre + "window"]), (k, trk.__targetWindowSize__)
+        H = g[pre + "hist"]
+        for i, h in enumerate(hist):
+            assert h == list(H[i, :len(h)]), (k, i, h, H[i])
+            assert len(h) == np.sum(H[i] >= 0)
+        np.testing.assert_allclose([n.cumulativeNLLR for n in nodes], g[pre + "cnllr"], rtol=RTOL, atol=ATOL)
+        nleaves = [len(trk.getLeafNodes(i)[1]) for i in range(len(nodes))]
+        assert nleaves == list(g[pre + "nleaves"]), k
+        assert info["n_clusters"] == int(g[pre + "nclusters"])
 
 
 @pytest.mark.parametrize("name", ["cfg3_head", "cfg3_lowclutter"])
