@@ -183,6 +183,11 @@ int64_t mht_forest_bytes(const mht_forest *f);
 /* Tracker.initiateTarget (tracker.py:147-160): new single-node tree; returns its slot in *slot. */
 int mht_forest_initiate(mht_forest *f, const double x0[4], const float P0[16], double Pd, int32_t *slot);
 
+/* The host is done with a DEAD track's slot (it has read the history it wants to keep): the slot and the host-side
+ * records behind it are recycled by a later mht_forest_initiate, so max_trees bounds the LIVE tracks, not the tracks
+ * ever initiated (the reference has no such limit at all). */
+int mht_forest_release(mht_forest *f, int32_t slot);
+
 /* One Tracker.addMeasurementList hot path.  h_z[M,2] f64 host (pinned or pageable), copied H2D on
  * the forest's stream; returns after the per-track results are back on the host.
  * h_meas_used[M] (may be NULL) receives the used-measurement mask of tracker.py:331-332. */
@@ -251,6 +256,12 @@ int mht_forest_tracks(mht_forest *f, int32_t cap, int32_t *n, int32_t *h_slot, d
  * (h_x[n,4], h_cnllr[n], h_P[n,16]) along it, initial node included.  Oldest first. */
 int mht_forest_history(mht_forest *f, int32_t slot, int32_t cap, int32_t *n, int32_t *h_meas, double *h_x,
                        double *h_cnllr, float *h_P);
+
+/* The same for EVERY live track with a handful of launches (helpFunctions.backtrackMeasurementNumbers over all tracks):
+ * row i of the [cap_tracks][cap_len] output arrays belongs to slot h_slot[i] and holds h_len[i] nodes, oldest first.
+ * MHT_E_CAPACITY: *n_tracks holds the number of live tracks (cap_tracks too small) or the longest history (cap_len). */
+int mht_forest_histories(mht_forest *f, int32_t cap_tracks, int32_t cap_len, int32_t *n_tracks, int32_t *h_slot,
+                         int32_t *h_len, int32_t *h_meas, double *h_x, double *h_cnllr, float *h_P);
 
 /* Smallest distance from (px,py) to any live leaf's position: the test of
  * Target.haveNoNeightbours (pymht/pyTarget.py:181-189) used by Tracker.initiateTarget. */

@@ -76,6 +76,7 @@ _SIGNATURES = {
     "mht_forest_destroy": (None, [_vp]),
     "mht_forest_bytes": (_i64, [_vp]),
     "mht_forest_initiate": (C.c_int, [_vp, _vp, _vp, _dbl, C.POINTER(_i32)]),
+    "mht_forest_release": (C.c_int, [_vp, _i32]),
     "mht_forest_scan": (C.c_int, [_vp, _i64, _vp, _dbl, C.POINTER(ScanInfo), _vp]),
     "mht_forest_scan_device": (C.c_int, [_vp, _i64, _vp, _dbl, C.POINTER(ScanInfo)]),
     "mht_forest_grow": (C.c_int, [_vp, _i64, _vp, _i32, _dbl, C.POINTER(ScanInfo), _vp]),
@@ -85,6 +86,7 @@ _SIGNATURES = {
     "mht_forest_set_dynamic_window": (C.c_int, [_vp, _i32, _i32, _i32]),
     "mht_forest_windows": (C.c_int, [_vp, _i32, C.POINTER(_i32), _vp, _vp]),
     "mht_forest_history": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i32), _vp, _vp, _vp, _vp]),
+    "mht_forest_histories": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i32), _vp, _vp, _vp, _vp, _vp, _vp]),
     "mht_forest_min_leaf_distance": (C.c_int, [_vp, _dbl, _dbl, C.POINTER(_dbl)]),
     "mht_forest_leaves": (C.c_int, [_vp, _i32, _i64, C.POINTER(_i64), _vp, _vp, _vp]),
 }

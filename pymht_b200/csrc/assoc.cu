@@ -2103,6 +2103,7 @@ struct DeviceCtx {
         s.best_targ = (int *)take(4ull * b->max_trees);
         s.cand_d = (double *)take(8ull * b->max_trees);
         s.cand_r = (int *)take(4ull * b->max_trees);
+        s.alive2 = (unsigned *)take(4ull * ((b->max_cols + 31) / 32));
         const size_t need = (8ull * p.nR + 15) / 16 * 16 + (4ull * p.nR + 15) / 16 * 16 + (8ull * p.nT + 15) / 16 * 16 +
                             (4ull * p.nT + 15) / 16 * 16 + (4ull * p.nwords + 15) / 16 * 16;
         if (need <= smem_bytes) {
@@ -2128,10 +2129,11 @@ __host__ __device__ inline long long bb_scratch_bytes(long long max_cols, long l
     auto al16 = [](long long v) { return (v + 15) / 16 * 16; };
     return al16(8 * max_cols) + al16(4 * max_cols) + al16(8 * max_rows) + al16(4 * max_trees) + al16(8 * max_trees) +
            al16(4 * max_trees) + al16(8 * max_rows) + al16(8 * max_trees) + al16(4 * max_rows) + al16(4 * max_trees) +
-           al16(4 * ((max_cols + 31) / 32)) + 256;
+           2 * al16(4 * ((max_cols + 31) / 32)) + 256;
 }
 
-__global__ void __launch_bounds__(kBBThreads, 1) bb_search_kernel(AssocWork w, int K_root, int K_node, int max_nodes) {
+__global__ void __launch_bounds__(kBBThreads, 1) bb_search_kernel(AssocWork w, int K_root, int K_node, int max_nodes,
+                                                                  int sb_cands, int sb_iters) {
     extern __shared__ __align__(16) unsigned char bb_smem[];
     __shared__ double red_d[64];
     __shared__ long long red_l[32];
@@ -2150,7 +2152,7 @@ __global__ void __launch_bounds__(kBBThreads, 1) bb_search_kernel(AssocWork w, i
     ctx.b = &b;
     bb::Scratch s;
     bb::Pool pl = *b.pool;
-    bb::worker(ctx, b.comps, pl, s, K_root, K_node, max_nodes);
+    bb::worker(ctx, b.comps, pl, s, K_root, K_node, max_nodes, sb_cands, sb_iters);
 }
 
 // results of the search: selection of every searched component, proven flags
@@ -2600,6 +2602,8 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
         static const int k_root = getenv("MHT_BB_KROOT") ? atoi(getenv("MHT_BB_KROOT")) : 200;
         static const int k_node = getenv("MHT_BB_KNODE") ? atoi(getenv("MHT_BB_KNODE")) : 60;
         static const double env_ms = getenv("MHT_BB_MS") ? atof(getenv("MHT_BB_MS")) : -1.0;
+        static const int sb_cands = getenv("MHT_BB_SB") ? atoi(getenv("MHT_BB_SB")) : 0;      // strong-branching probes
+        static const int sb_iters = getenv("MHT_BB_SB_ITERS") ? atoi(getenv("MHT_BB_SB_ITERS")) : 15;
         const double ms = env_ms >= 0.0 ? env_ms : exact_ms;
         if (ev && ev->exact_begin) MHT_CUDA(cudaEventRecord(ev->exact_begin, s));
         // a dual iteration on n columns costs ~n / 4e9 s in one CTA: components the time box cannot even evaluate
@@ -2619,7 +2623,8 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
                 if (smem_bytes < 32768) smem_bytes = 32768;
                 MHT_CUDA(cudaFuncSetAttribute(bb_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
             }
-            count_launch(), bb_search_kernel<<<kBBWorkers, kBBThreads, smem_bytes, s>>>(w, k_root, k_node, exact_nodes);
+            count_launch(), bb_search_kernel<<<kBBWorkers, kBBThreads, smem_bytes, s>>>(w, k_root, k_node, exact_nodes, sb_cands,
+                                                                                        sb_iters);
             count_launch(), bb_writeback_kernel<<<kSMs, 256, 0, s>>>(c, w);
             count_launch(), bb_state_kernel<<<4, 256, 0, s>>>(w);
         }

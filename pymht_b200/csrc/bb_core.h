@@ -73,6 +73,7 @@ struct Scratch {
     int *best_targ;              // [nT]
     double *cand_d;              // [nT] branching candidate per tree: distance of y from 1/2
     int *cand_r;                 // [nT] ... and its row
+    unsigned *alive2;            // [nwords] alive mask of a probed child (strong branching)
 };
 
 struct EvalResult {
@@ -162,10 +163,109 @@ BB_HD inline void offer_incumbent(Ctx &c, const Comp &p, const Scratch &s, doubl
     c.sync();
 }
 
+// Strong-branching probe: bound of the child (t, r, type) of the node whose alive mask is s.alive and whose best
+// multipliers are s.ubest, after K iterations.  Uses s.alive2 / s.u / s.rc / s.tmin / s.targ / s.usage as scratch;
+// s.alive, s.ubest, s.best_targ stay untouched.  Returns 1e300 for an infeasible child.
+template <class Ctx>
+BB_HD inline double probe_child(Ctx &c, const Comp &p, Scratch &s, int t, int r, int type, int K, double ub) {
+    for (int w = c.tid(); w < p.nwords; w += c.nthr()) {
+        unsigned m = s.alive[w];
+        unsigned out = m;
+        for (int b = 0; b < 32 && m; ++b) {
+            if (!((m >> b) & 1u)) continue;
+            const int j = w * 32 + b;
+            const bool mine = p.tree[j] == t;
+            if (type == 0 && !mine) continue;
+            const bool uses = col_uses<Ctx>(p, j, r);
+            const bool dead = type == 0 ? uses : (mine ? !uses : uses);
+            if (dead) out &= ~(1u << b);
+        }
+        s.alive2[w] = out;
+    }
+    for (int q = c.tid(); q < p.nR; q += c.nthr()) s.u[q] = s.ubest[q];
+    c.sync();
+    double bestL = -1e300, theta = 1.0;
+    int stall = 0;
+    for (int it = 0; it < K; ++it) {
+        for (int q = c.tid(); q < p.nT; q += c.nthr()) s.tmin[q] = kInfKey;
+        for (int q = c.tid(); q < p.nR; q += c.nthr()) s.usage[q] = 0;
+        c.sync();
+        for (int j = c.tid(); j < p.nC; j += c.nthr()) {
+            if (!((s.alive2[j >> 5] >> (j & 31)) & 1u)) continue;
+            double v = p.cost[j];
+            for (int k = 0; k < p.W; ++k) {
+                const int q = p.rows[(long long)k * p.row_stride + j];
+                if (q >= 0) v += s.u[q];
+            }
+            s.rc[j] = v;
+            const unsigned long long key = key_of(v);
+            const int tt = p.tree[j];
+            if (key < *(volatile unsigned long long *)&s.tmin[tt]) c.amin64(&s.tmin[tt], key);
+        }
+        c.sync();
+        // usage of the argmins: every column that attains its tree's minimum counts once per tree (ties are rare and
+        // only perturb the direction, never the bound)
+        for (int q = c.tid(); q < p.nT; q += c.nthr()) s.targ[q] = -1;
+        c.sync();
+        for (int j = c.tid(); j < p.nC; j += c.nthr()) {
+            if (!((s.alive2[j >> 5] >> (j & 31)) & 1u)) continue;
+            if (key_of(s.rc[j]) == s.tmin[p.tree[j]]) c.amax(&s.targ[p.tree[j]], j);
+        }
+        c.sync();
+        double lsum = 0.0, dummy = 0.0;
+        long long dead = 0;
+        for (int q = c.tid(); q < p.nT; q += c.nthr()) {
+            const int j = s.targ[q];
+            if (j < 0) {
+                dead = 1;
+                continue;
+            }
+            lsum += of_key(s.tmin[q]);
+            for (int k = 0; k < p.W; ++k) {
+                const int rr = p.rows[(long long)k * p.row_stride + j];
+                if (rr >= 0) c.aadd(&s.usage[rr], 1);
+            }
+        }
+        unsigned long long x = 0;
+        c.reduce(lsum, dummy, dead, x);
+        if (dead) return 1e300;
+        double usum = 0.0, nrm = 0.0;
+        long long worst = 0;
+        for (int q = c.tid(); q < p.nR; q += c.nthr()) {
+            int g = s.usage[q] - 1;
+            const double ur = s.u[q];
+            if (ur <= 0.0 && g < 0) g = 0;
+            usum += ur;
+            nrm += (double)(g * g);
+        }
+        c.reduce(usum, nrm, worst, x);
+        const double L = lsum - usum;
+        if (L > bestL + 1e-12) {
+            bestL = L;
+            stall = 0;
+        } else if (++stall >= 3) {
+            theta *= 0.7;
+            stall = 0;
+        }
+        if (nrm == 0.0 || bestL >= ub - kPruneEps) break;
+        const double step = theta * (ub - L) / nrm;
+        for (int q = c.tid(); q < p.nR; q += c.nthr()) {
+            int g = s.usage[q] - 1;
+            const double ur = s.u[q];
+            if (ur <= 0.0 && g < 0) g = 0;
+            const double v = ur + step * (double)g;
+            s.u[q] = v > 0.0 ? v : 0.0;
+        }
+        c.sync();
+    }
+    c.sync();
+    return bestL;
+}
+
 // K subgradient iterations on the alive columns, starting from s.u.  On return: s.ubest / s.best_targ hold the
 // best iterate, s.alive has lost the columns fixed out at the best iterate, res has bound / branching pair.
 template <class Ctx>
-BB_HD inline void evaluate(Ctx &c, const Comp &p, Scratch &s, int K, EvalResult &res) {
+BB_HD inline void evaluate(Ctx &c, const Comp &p, Scratch &s, int K, EvalResult &res, int sb_cands = 0, int sb_iters = 15) {
     double bestL = -1e300, theta = 1.0;
     int stall = 0, it = 0;
     bool solved = false, infeasible = false, aborted = false;
@@ -360,10 +460,52 @@ BB_HD inline void evaluate(Ctx &c, const Comp &p, Scratch &s, int K, EvalResult 
             if (key > best) best = key;
         }
         best = c.maxll(best);
-        if (best >= 0) {
+        if (best >= 0 && sb_cands <= 1) {
             res.bt = 0x7fffffff - (int)(best & 0xffffffffll);
             res.br = s.cand_r[res.bt];
             return;
+        }
+        if (best >= 0) {
+            // ---- strong branching: probe the sb_cands most fractional pairs, keep the one whose weaker child gains
+            //      most (a pruned / infeasible child counts as the whole gap) ----
+            double best_score = -1.0;
+            int best_t = -1, best_r = -1;
+            for (int cand = 0; cand < sb_cands; ++cand) {
+                long long pick = -1;
+                for (int t = c.tid(); t < p.nT; t += c.nthr()) {
+                    if (s.cand_r[t] < 0 || s.cand_d[t] >= 0.5 - 1e-9) continue;
+                    const long long q = (long long)((0.5 - s.cand_d[t]) * 1048576.0);
+                    const long long key = (q << 32) | (long long)(0x7fffffff - t);
+                    if (key > pick) pick = key;
+                }
+                pick = c.maxll(pick);
+                if (pick < 0) break;
+                const int t = 0x7fffffff - (int)(pick & 0xffffffffll);
+                const int r = s.cand_r[t];
+                c.sync();
+                if (c.tid() == 0) s.cand_d[t] = 1.0;      // taken
+                c.sync();
+                const double gap_now = ub - bestL;
+                double g0 = probe_child(c, p, s, t, r, 0, sb_iters, ub) - bestL;
+                double g1 = probe_child(c, p, s, t, r, 1, sb_iters, ub) - bestL;
+                if (g0 > gap_now) g0 = gap_now;
+                if (g1 > gap_now) g1 = gap_now;
+                if (g0 < 1e-6) g0 = 1e-6;
+                if (g1 < 1e-6) g1 = 1e-6;
+                const double score = g0 * g1;
+                if (score > best_score) {
+                    best_score = score;
+                    best_t = t;
+                    best_r = r;
+                }
+                if (bcast0(c, c.expired() ? 1 : 0)) break;
+            }
+            // the probes used s.u as scratch: the node's multipliers are s.ubest (what store_node keeps)
+            for (int q = c.tid(); q < p.nR; q += c.nthr()) s.u[q] = s.ubest[q];
+            c.sync();
+            res.bt = best_t;
+            res.br = best_r;
+            if (best_t >= 0) return;
         }
     }
     // ---- fallbacks (the choices were stable over the second half) ----
@@ -534,7 +676,7 @@ BB_HD inline void store_node(Ctx &c, const Comp &p, Pool &pl, int slot, int comp
 // this worker continues with (taken), or -1.
 template <class Ctx>
 BB_HD inline int expand(Ctx &c, const Comp *comps, Pool &pl, int cur, Scratch &s, int K_root, int K_node,
-                        int max_nodes) {
+                        int max_nodes, int sb_cands = 0, int sb_iters = 15) {
     const int ci = ((volatile int *)pl.comp)[cur];
     const Comp &p = comps[ci];
     const double pbound = ((volatile double *)pl.bound)[cur];
@@ -572,7 +714,7 @@ BB_HD inline int expand(Ctx &c, const Comp *comps, Pool &pl, int cur, Scratch &s
         c.sync();
         apply_decision(c, p, s, pbt, pbr, root ? -1 : ch);
         EvalResult res;
-        evaluate(c, p, s, root ? K_root : K_node, res);
+        evaluate(c, p, s, root ? K_root : K_node, res, sb_cands, sb_iters);
         if (c.tid() == 0) {
             c.aadd(pl.nodes, 1);
             c.aadd(pl.iters, res.iters);
@@ -631,7 +773,8 @@ BB_HD inline int expand(Ctx &c, const Comp *comps, Pool &pl, int cur, Scratch &s
 
 // One worker (a CTA): claim the most promising open node, dive from it, repeat until the pool drains.
 template <class Ctx>
-BB_HD inline void worker(Ctx &c, const Comp *comps, Pool &pl, Scratch &s, int K_root, int K_node, int max_nodes) {
+BB_HD inline void worker(Ctx &c, const Comp *comps, Pool &pl, Scratch &s, int K_root, int K_node, int max_nodes,
+                         int sb_cands = 0, int sb_iters = 15) {
     while (true) {
         if (bcast0(c, *(volatile int *)pl.stop)) break;
         int cur = claim_best(c, pl);
@@ -651,7 +794,7 @@ BB_HD inline void worker(Ctx &c, const Comp *comps, Pool &pl, Scratch &s, int K_
                 c.sync();
                 break;
             }
-            cur = expand(c, comps, pl, cur, s, K_root, K_node, max_nodes);
+            cur = expand(c, comps, pl, cur, s, K_root, K_node, max_nodes, sb_cands, sb_iters);
             if (bcast0(c, *(volatile int *)pl.stop)) break;
         }
     }

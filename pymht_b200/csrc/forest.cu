@@ -120,6 +120,7 @@ struct mht_forest {
     std::vector<std::vector<TrunkNode>> trunk;
     int64_t h_level_nodes;     // nodes in the current level (for initiate)
     std::vector<int> last_tracks;  // tree slots reported by the last scan
+    std::vector<int> free_slots;   // slots of dead tracks the host has released (mht_forest_release): reused by initiate
     bool open_scan = false;        // mht_forest_grow done, mht_forest_select pending
     // dynamic window (Tracker.__dynamicWindow, tracker.py:918-950): size criterion on device, roof from the host
     int dyn_window = 0, target_size_limit = 3000, window_roof = 0;
@@ -1556,12 +1557,18 @@ extern "C" int mht_forest_initiate(mht_forest *f, const double x0[4], const floa
         set_error("mht_forest_initiate: invalid argument");
         return MHT_E_INVALID;
     }
-    if (f->T >= f->cfg.max_trees || f->h_level_nodes >= f->cap_nodes) {
-        set_error("mht_forest_initiate: capacity exceeded (trees %d/%d)", f->T, f->cfg.max_trees);
+    if ((f->T >= f->cfg.max_trees && f->free_slots.empty()) || f->h_level_nodes >= f->cap_nodes) {
+        set_error("mht_forest_initiate: capacity exceeded (trees %d/%d, no released slot)", f->T, f->cfg.max_trees);
         return MHT_E_CAPACITY;
     }
     cudaStream_t s = f->stream;
-    const int t = f->T;
+    // a released slot of a dead track first (lowest index: deterministic), a fresh one otherwise
+    int t = f->T;
+    if (!f->free_slots.empty()) {
+        auto it = std::min_element(f->free_slots.begin(), f->free_slots.end());
+        t = *it;
+        f->free_slots.erase(it);
+    }
     const Level &L = f->lv[f->scan % f->nslots];
     const int pos = (int)f->h_level_nodes, pi = 0;
     const unsigned short pat0 = 0;
@@ -1602,8 +1609,23 @@ extern "C" int mht_forest_initiate(mht_forest *f, const double x0[4], const floa
     memcpy(nd.P, P0, sizeof(nd.P));
     f->trunk[t].clear();
     f->trunk[t].push_back(nd);
-    f->T = t + 1;
+    f->dead_hist[t].clear();
+    if (t == f->T) f->T = t + 1;
     if (slot) *slot = t;
+    return MHT_OK;
+}
+
+extern "C" int mht_forest_release(mht_forest *f, int32_t slot) {
+    if (!f || slot < 0 || slot >= f->T || f->h_alive[slot]) {
+        set_error("mht_forest_release: slot %d is not a dead track's slot", slot);
+        return MHT_E_INVALID;
+    }
+    if (std::find(f->free_slots.begin(), f->free_slots.end(), slot) != f->free_slots.end()) return MHT_OK;
+    f->trunk[slot].clear();
+    f->trunk[slot].shrink_to_fit();
+    f->dead_hist[slot].clear();
+    f->dead_hist[slot].shrink_to_fit();
+    f->free_slots.push_back(slot);
     return MHT_OK;
 }
 
@@ -1805,6 +1827,84 @@ extern "C" int mht_forest_history(mht_forest *f, int32_t slot, int32_t cap, int3
         if (h_x) memcpy(h_x + 4 * i, o + 2, 32);
         if (h_P)
             for (int q = 0; q < 16; ++q) h_P[16 * i + q] = (float)o[8 + q];
+    }
+    return MHT_OK;
+}
+
+// mht_forest_history for EVERY live track in one go: the window walks of all tracks share kDeadChunk-wide launches
+// (4 launches for 1000 tracks instead of 1000 single-thread launches with a stream sync each).
+extern "C" int mht_forest_histories(mht_forest *f, int32_t cap_tracks, int32_t cap_len, int32_t *n_tracks,
+                                    int32_t *h_slot, int32_t *h_len, int32_t *h_meas, double *h_x, double *h_cnllr,
+                                    float *h_P) {
+    if (!f || !n_tracks || !h_slot || !h_len || cap_len < 1) {
+        set_error("mht_forest_histories: invalid argument");
+        return MHT_E_INVALID;
+    }
+    std::vector<int> live;
+    for (int t = 0; t < f->T; ++t)
+        if (f->h_alive[t]) live.push_back(t);
+    *n_tracks = (int)live.size();
+    if ((int)live.size() > cap_tracks) {
+        set_error("mht_forest_histories: %d live tracks exceed cap %d", (int)live.size(), cap_tracks);
+        return MHT_E_CAPACITY;
+    }
+    cudaStream_t s = f->stream;
+    UpdateArgs ub;
+    fill_update_args(f, &ub);
+    int need = 0;
+    for (size_t lo = 0; lo < live.size(); lo += kDeadChunk) {
+        const int n = (int)std::min<size_t>(kDeadChunk, live.size() - lo);
+        int n_walk = 0;
+        for (int i = 0; i < n; ++i) {
+            const int t = live[lo + i];
+            f->dead_h[i] = t;
+            f->dead_h[kDeadChunk + i] = f->h_last_pos[t];
+            if (f->h_last_pos[t] >= 0 && f->scan > f->h_root_scan[t]) ++n_walk;
+        }
+        if (n_walk) {
+            MHT_CUDA(cudaMemcpyAsync(f->dead_d, f->dead_h, sizeof(int) * 2 * kDeadChunk, cudaMemcpyHostToDevice, s));
+            count_launch(), history_batch_kernel<<<(n + 63) / 64, 64, 0, s>>>(ub, f->dead_d, n, f->scan, f->histb_d);
+            MHT_CUDA(cudaGetLastError());
+            MHT_CUDA(cudaMemcpyAsync(f->histb_h, f->histb_d, sizeof(double) * (size_t)n * kHistStride,
+                                     cudaMemcpyDeviceToHost, s));
+            MHT_CUDA(cudaStreamSynchronize(s));
+        }
+        for (int i = 0; i < n; ++i) {
+            const int t = live[lo + i];
+            const size_t row = lo + i;
+            const std::vector<TrunkNode> &tr = f->trunk[t];
+            const bool walk = f->h_last_pos[t] >= 0 && f->scan > f->h_root_scan[t];
+            const double *o0 = f->histb_h + (size_t)i * kHistStride;
+            const int wn = walk ? (int)o0[0] : 0;
+            const int total = (int)tr.size() + wn;
+            h_slot[row] = t;
+            h_len[row] = total;
+            need = std::max(need, total);
+            if (total > cap_len) continue;
+            int k = 0;
+            for (const TrunkNode &nd : tr) {
+                const size_t e = row * cap_len + k;
+                if (h_meas) h_meas[e] = nd.meas;
+                if (h_x) memcpy(h_x + 4 * e, nd.x, 32);
+                if (h_cnllr) h_cnllr[e] = nd.cnllr;
+                if (h_P) memcpy(h_P + 16 * e, nd.P, 64);
+                ++k;
+            }
+            for (int q = wn - 1; q >= 0; --q, ++k) {   // the walk is leaf -> root; report oldest first
+                const double *o = o0 + kHistRec + kHistRec * q;
+                const size_t e = row * cap_len + k;
+                if (h_meas) h_meas[e] = (int)o[0];
+                if (h_cnllr) h_cnllr[e] = o[1];
+                if (h_x) memcpy(h_x + 4 * e, o + 2, 32);
+                if (h_P)
+                    for (int z = 0; z < 16; ++z) h_P[16 * e + z] = (float)o[8 + z];
+            }
+        }
+    }
+    if (need > cap_len) {
+        set_error("mht_forest_histories: the longest history has %d nodes, cap_len is %d", need, cap_len);
+        *n_tracks = need;      // the caller retries with this length
+        return MHT_E_CAPACITY;
     }
     return MHT_OK;
 }

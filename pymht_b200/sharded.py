@@ -92,6 +92,7 @@ class ShardedTracker(Tracker):
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self._device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
         super().__init__(model, radarPeriod, lambda_phi, lambda_nu, **kwargs)
+        self._recycle_slots = False    # slot s of rank r is global tree tree_off[r] + s on every rank: never renumbered
         self.exchangeLog = []          # per scan: dict(n_cols_global, bytes_gathered, ms_exchange, ms_solve)
         self._buf = {}                 # persistent device buffers (grown geometrically, never per scan)
         self._solve_geometry = None    # (cap_cols, n_tree_slots, n_rows) of the workspace holding warm multipliers

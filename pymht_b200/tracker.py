@@ -93,6 +93,7 @@ class Tracker:
         self._slot_info = {}                # slot -> initial Target of the track
         self._last = None                   # per-track arrays of the last scan
         self._live_rows = None
+        self._recycle_slots = True          # the tree-sharded tracker keeps slot numbers stable across ranks instead
         self._create_forest()
 
     # ------------------------------------------------------------------------------------------
@@ -246,13 +247,24 @@ class Tracker:
         _lib.check(self._lib.mht_forest_tracks(self._forest, cap, C.byref(n), _lib.ptr(slot), _lib.ptr(x), _lib.ptr(P),
                                                _lib.ptr(cn), _lib.ptr(meas), _lib.ptr(status)))
         k = n.value
-        assert k == len(self._slots) and np.array_equal(slot[:k], self._slots), "forest/track bookkeeping out of sync"
+        # the forest reports in slot order; tracks keep the reference's order (creation order, tracker.py:147-160),
+        # which differs once a released slot has been reused
+        assert k == len(self._slots) and sorted(slot[:k].tolist()) == sorted(self._slots), \
+            "forest/track bookkeeping out of sync"
+        if not np.array_equal(slot[:k], self._slots):
+            row_of = {int(sl): r for r, sl in enumerate(slot[:k])}
+            order = np.array([row_of[sl] for sl in self._slots], dtype=np.int64)
+            x, P, cn, meas, status = x[order], P[order], cn[order], meas[order], status[order]
         self._last = (scanList, len(self.__scanHistory__), x, P, cn, meas, status)
         dead = np.flatnonzero(status[:k] != 0)
         for i in dead:
-            # the library keeps the window records of a track that died (mht_forest_history serves them from
-            # the host), so a terminated track's parent chain stays lazy like a live one's
-            self.__terminatedTargets__.append(self._make_node(int(i), self._slots[i], dead=True))
+            # the library keeps the window records of a track that died this scan (mht_forest_history serves them
+            # from the host): read them now, then hand the slot back so that a later initiation can reuse it
+            hist = None
+            if self._recycle_slots:
+                hist = self._history(self._slots[i])          # raw arrays (host copy, no launch); Targets stay lazy
+                _lib.check(self._lib.mht_forest_release(self._forest, int(self._slots[i])))
+            self.__terminatedTargets__.append(self._make_node(int(i), self._slots[i], dead=True, hist=hist))
         if len(dead):
             keep = [i for i in range(k) if status[i] == 0]
             self._slots = [self._slots[i] for i in keep]
@@ -273,16 +285,48 @@ class Tracker:
         by_slot = dict(zip(slot[:n.value].tolist(), win[:n.value].tolist()))
         self.__targetWindowSize__ = [by_slot.get(s, w) for s, w in zip(self._slots, self.__targetWindowSize__)]
 
-    def _make_node(self, row, slot, dead=False):
+    def _make_node(self, row, slot, dead=False, hist=None):
         scanList, scanNumber, x, P, cn, meas, status = self._last
         root = self._slot_info[slot]
         m = int(meas[row])
         return Target(scanList.time, scanNumber, x[row].copy(), P[row].copy(), ID=root.ID, P_d=root.P_d,
                       measurementNumber=m, measurement=(np.asarray(scanList.measurements)[m - 1] if m > 0 else None),
                       cumulativeNLLR=float(cn[row]), status=STATUS_TAGS[int(status[row])],
-                      parent_loader=self._make_parent_loader(slot, dead, self._window_of(slot)))
+                      parent_loader=self._make_parent_loader(slot, dead, self._window_of(slot), hist))
+
+    def _prefetch_histories(self):
+        """Histories of ALL live tracks in a handful of launches (mht_forest_histories); valid until the next scan."""
+        n_live = max(len(self._slots), 1)
+        cap_len = 64
+        for attempt in range(4):
+            n = C.c_int32()
+            slot = np.zeros(n_live, dtype=np.int32)
+            ln = np.zeros(n_live, dtype=np.int32)
+            meas = np.zeros((n_live, cap_len), dtype=np.int32)
+            x = np.zeros((n_live, cap_len, 4), dtype=np.float64)
+            cn = np.zeros((n_live, cap_len), dtype=np.float64)
+            P = np.zeros((n_live, cap_len, 4, 4), dtype=np.float32)
+            rc = self._lib.mht_forest_histories(self._forest, n_live, cap_len, C.byref(n), _lib.ptr(slot), _lib.ptr(ln),
+                                                _lib.ptr(meas), _lib.ptr(x), _lib.ptr(cn), _lib.ptr(P))
+            if rc == _lib.MHT_E_CAPACITY and attempt < 3:     # cap_tracks is exact, so the histories are longer
+                cap_len = max(n.value, cap_len) + 8
+                continue
+            _lib.check(rc)
+            break
+        self._hist_cache = (len(self.__scanHistory__),
+                            {int(s): (meas[i, :ln[i]], x[i, :ln[i]], cn[i, :ln[i]], P[i, :ln[i]])
+                             for i, s in enumerate(slot[:n.value])})
 
     def _history(self, slot):
+        cache = getattr(self, "_hist_cache", None)
+        if cache is not None and cache[0] == len(self.__scanHistory__) and slot in cache[1]:
+            return cache[1][slot]
+        if slot in self._slots and len(self._slots) > 8:
+            # a live track's history is wanted: fetch every live track's at once, the callers that walk parents
+            # (helpFunctions.backtrackMeasurementNumbers, plotting) go over all tracks
+            self._prefetch_histories()
+            if slot in self._hist_cache[1]:
+                return self._hist_cache[1][slot]
         cap = 64
         while True:
             n = C.c_int32()
@@ -305,16 +349,16 @@ class Tracker:
         except ValueError:      # the track died this scan: it was not pruned
             return self.N
 
-    def _make_parent_loader(self, slot, dead=False, window=None):
+    def _make_parent_loader(self, slot, dead=False, window=None, hist=None):
         scan_at_creation = len(self.__scanHistory__)
         window = self.N if window is None else max(0, window)
+        root = self._slot_info[slot]          # bound now: the slot may be reused by a later track
 
         def load(leaf):
             if not dead and len(self.__scanHistory__) != scan_at_creation:
                 raise RuntimeError("Target.parent must be materialised before the next scan is added "
                                    "(the window nodes live on the device)")
-            meas, x, cn, P = self._history(slot)
-            root = self._slot_info[slot]
+            meas, x, cn, P = hist if hist is not None else self._history(slot)
             first_scan = root.scanNumber
             # current root of the tree: N scans above the leaf once the window is full (tracker.py:1219-1231);
             # a track terminated this scan was not pruned, its root is one scan older

@@ -29,7 +29,8 @@ struct HostCtx {
 // then the first column of every tree must be row-free).  Returns 1 when the optimum is proven.
 extern "C" int bb_solve_host(int nC, int nT, int nR, int W, const double *cost, const int *tree, const int *rows,
                              const double *u0, const int *sel0, int K_root, int K_node, int max_nodes, int pool_cap,
-                             int *best_sel, double *best, int *nodes, int *iters) {
+                             int *best_sel, double *best, int *nodes, int *iters, int sb_cands, int sb_iters,
+                             double *open_bound) {
     std::vector<int> tstart(nT + 1, 0);
     for (int j = 0; j < nC; ++j) tstart[tree[j] + 1] = j + 1;
     for (int t = 0; t < nT; ++t) if (tstart[t + 1] < tstart[t]) tstart[t + 1] = tstart[t];
@@ -50,11 +51,11 @@ extern "C" int bb_solve_host(int nC, int nT, int nR, int W, const double *cost, 
     std::vector<double> su(nR), rc(nC), ubest(nR), cand_d(nT);
     std::vector<int> usage(nR), targ(nT), freq(nC), best_targ(nT), cand_r(nT);
     std::vector<unsigned long long> tmin(nT);
-    std::vector<unsigned> alive(p.nwords);
+    std::vector<unsigned> alive(p.nwords), alive2(p.nwords);
     bb::Scratch s;
     s.u = su.data(); s.usage = usage.data(); s.tmin = tmin.data(); s.targ = targ.data(); s.alive = alive.data();
     s.rc = rc.data(); s.freq = freq.data(); s.ubest = ubest.data(); s.best_targ = best_targ.data();
-    s.cand_d = cand_d.data(); s.cand_r = cand_r.data();
+    s.cand_d = cand_d.data(); s.cand_r = cand_r.data(); s.alive2 = alive2.data();
     bb::Pool pl;
     pl.cap = pool_cap; pl.node_words = p.nwords; pl.node_rows = nR > 0 ? nR : 1;
     std::vector<int> state(pool_cap, 0), comp(pool_cap), bt(pool_cap), br(pool_cap);
@@ -74,7 +75,13 @@ extern "C" int bb_solve_host(int nC, int nT, int nR, int W, const double *cost, 
     }
     for (int r = 0; r < nR; ++r) pu[r] = u0 ? (float)u0[r] : 0.0f;
     HostCtx c;
-    bb::worker(c, &p, pl, s, K_root, K_node, max_nodes);
+    bb::worker(c, &p, pl, s, K_root, K_node, max_nodes, sb_cands, sb_iters);
+    if (open_bound) {
+        double lo = 1e300;
+        for (int i = 0; i < pool_cap; ++i)
+            if (state[i] != 0 && bound[i] < lo) lo = bound[i];
+        *open_bound = lo;
+    }
     for (int t = 0; t < nT; ++t) best_sel[t] = bsel[t];
     *best = bb::of_key(ub_key);
     *nodes = n_nodes;

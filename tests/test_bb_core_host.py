@@ -20,7 +20,8 @@ def bb_lib(tmp_path_factory):
     subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", out, os.path.join(ROOT, "tests", "host", "bb_host.cpp")])
     lib = C.CDLL(out)
     lib.bb_solve_host.argtypes = ([C.c_int] * 4 + [C.c_void_p] * 5 + [C.c_int] * 4 +
-                                  [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)])
+                                  [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                   C.c_int, C.c_int, C.POINTER(C.c_double)])
     return lib
 
 
@@ -61,7 +62,7 @@ def _solve(bb_lib, trk, cl, max_nodes=200000, pool=20000):
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     proven = bb_lib.bb_solve_host(n, nT, max(nr, 1), W, p(cost), p(np.ascontiguousarray(ct, dtype=np.int32)),
                                   p(np.ascontiguousarray(RM)), None, None, 200, 60, max_nodes, pool, p(best_sel),
-                                  C.byref(best), C.byref(nn), C.byref(it))
+                                  C.byref(best), C.byref(nn), C.byref(it), 0, 15, None)
     rows_used = RM[:, best_sel][RM[:, best_sel] >= 0]
     feasible = len(rows_used) == len(set(rows_used.tolist())) and list(np.asarray(ct)[best_sel]) == list(range(nT))
     return proven, best.value, float(cost[best_sel].sum()), feasible, nn.value, (cost, ct, ptr, idx, nT, nr)

@@ -199,6 +199,28 @@ def test_tracker_replays_reference_golden(name):
         trk._checkTrackerIntegrity()
 
 
+def test_tracker_cfg5_full_vs_reference():
+    """BASELINE config 5 at full size: 500 targets, 50 pairs crossing at 90 degrees on the same scan (less than a
+    gate radius apart for +-2 scans), 400 background targets, lambda = 1e-4, N = 8 -- the six scans the reference
+    finishes (scan 6: 8.6e4 leaves in ONE 490-tree cluster, 65 s of the reference's time).  Every scan must be
+    certified and identical to the reference."""
+    for k, g, pre, trk, nodes, hist, info in _replay_tracker("cfg5_full", maxTargets=1024, maxNodes=1 << 21,
+                                                             maxParents=1 << 19, exactBudgetMs=30000):
+        print("cfg5_full scan", k + 1, {kk: info[kk] for kk in ("n_parents", "n_children", "n_clusters", "certified",
+                                                                "n_candidates", "max_component", "bb_nodes", "lower_bound",
+                                                                "objective", "ms_gate", "ms_assoc")})
+        assert info["certified"] == 1, (k, info)
+        assert [n.ID for n in nodes] == list(g[pre + "ids"]), k
+        H = g[pre + "hist"]
+        for i, h in enumerate(hist):
+            assert h == list(H[i, :len(h)]), (k, i, h, H[i])
+        np.testing.assert_allclose([n.cumulativeNLLR for n in nodes], g[pre + "cnllr"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(np.array([n.x_0 for n in nodes]).reshape(-1, 4), g[pre + "x"], rtol=RTOL, atol=XATOL)
+        nleaves = [len(trk.getLeafNodes(i)[1]) for i in range(len(nodes))]
+        assert nleaves == list(g[pre + "nleaves"]), k
+        assert info["n_clusters"] == int(g[pre + "nclusters"])
+
+
 def test_dynamic_window_matches_reference():
     """addMeasurementList(dynamicWindow=True) (tracker.py:244-248,918-950): the reference ran this fixture with
     targetSizeLimit = 60 and its wall-clock criteria out of reach, so only the size criterion fires -- per-tree windows
@@ -461,3 +483,47 @@ def test_terminated_tracks_keep_their_history():
                 while n.parent is not None:
                     n, depth = n.parent, depth + 1
                 assert depth == len(h) and n.scanNumber + depth == t.scanNumber
+
+
+def test_tree_slots_are_recycled():
+    """max_trees must bound the LIVE tracks, not the tracks ever initiated.  8 slots, 40 births: tracks
+    born outside the radar range die in their first scan (OutOfRange, tracker.py:894-899), their slots are released
+    and reused; one long-lived track keeps its identity, order and history throughout."""
+    from pymht_b200.pyTarget import Target, backtrackMeasurementNumbers
+    from pymht_b200.utils.classDefinitions import MeasurementList
+    trk, pv = _small_tracker(maxTargets=8, radarRange=500.0)
+    trk.initiateTarget(Target(0.0, None, np.array([10.0, 10.0, 1.0, 0.0]), pv.P0))
+    born = 1
+    for k in range(10):
+        for q in range(4):
+            trk.initiateTarget(Target(2.5 * k, None, np.array([900.0 + 10 * q, 900.0, 0.0, 0.0]), pv.P0))
+            born += 1
+        z = np.array([[10.0 + 2.5 * (k + 1), 10.0]], dtype=np.float32)
+        trk.addMeasurementList(MeasurementList(2.5 * (k + 1), z))
+        nodes = trk.getTrackNodes()
+        assert [n.ID for n in nodes] == [0], (k, [n.ID for n in nodes])
+        assert nodes[0].measurementNumber == 1
+    assert born == 41 and len(trk.__terminatedTargets__) == 40
+    assert backtrackMeasurementNumbers(list(trk.getTrackNodes())) == [[1] * 10]
+    dead = trk.__terminatedTargets__[7]
+    assert dead.status == "OutOfRange" and dead.parent is not None and dead.parent.parent is None
+    trk.close()
+
+
+def test_histories_of_all_tracks_in_one_call():
+    """backtrackMeasurementNumbers over all tracks goes through ONE batched walk (mht_forest_histories: a launch per
+    256 tracks) instead of a single-thread launch + sync per track, and returns the reference's histories."""
+    from pymht_b200.pyTarget import backtrackMeasurementNumbers
+    checked = 0
+    for k, g, pre, trk, nodes, hist, info in _replay_tracker("cfg2", n_scans=6):
+        trk._hist_cache = None
+        trk.__trackNodes__ = None                       # fresh Target views with unloaded parents
+        l0 = trk._lib.mht_launch_count()
+        again = backtrackMeasurementNumbers(list(trk.getTrackNodes()))
+        launches = trk._lib.mht_launch_count() - l0
+        H = g[pre + "hist"]
+        for i, h in enumerate(again):
+            assert h == list(H[i, :len(h)]), (k, i)
+        assert len(nodes) > 50 and launches <= 2, (k, len(nodes), launches)
+        checked += 1
+    assert checked == 6

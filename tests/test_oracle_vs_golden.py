@@ -92,3 +92,9 @@ def test_replay_cfg3_head():
 def test_replay_cfg3_lowclutter():
     """1000 targets, 10x less clutter: scans 1-2 (scan 3 needs ~3 min of HiGHS; the GPU test replays it)."""
     replay("cfg3_lowclutter", n_scans=2)
+
+
+def test_replay_cfg5_full():
+    """BASELINE config 5 at full size (500 targets, 50 scripted 90-degree crossings, N = 8): scans 1-4 (scans 5-6
+    hold 3.4e4 / 8.6e4 leaves in one cluster -- minutes of HiGHS; the GPU test replays all six)."""
+    replay("cfg5_full", n_scans=4)
