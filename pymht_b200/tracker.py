@@ -262,7 +262,7 @@ class Tracker:
             # from the host): read them now, then hand the slot back so that a later initiation can reuse it
             hist = None
             if self._recycle_slots:
-                hist = self._history(self._slots[i])          # raw arrays (host copy, no launch); Targets stay lazy
+                hist = self._history(self._slots[i], prefetch=False)   # raw arrays (host copy, no launch); Targets stay lazy
                 _lib.check(self._lib.mht_forest_release(self._forest, int(self._slots[i])))
             self.__terminatedTargets__.append(self._make_node(int(i), self._slots[i], dead=True, hist=hist))
         if len(dead):
@@ -317,11 +317,11 @@ class Tracker:
                             {int(s): (meas[i, :ln[i]], x[i, :ln[i]], cn[i, :ln[i]], P[i, :ln[i]])
                              for i, s in enumerate(slot[:n.value])})
 
-    def _history(self, slot):
+    def _history(self, slot, prefetch=True):
         cache = getattr(self, "_hist_cache", None)
         if cache is not None and cache[0] == len(self.__scanHistory__) and slot in cache[1]:
             return cache[1][slot]
-        if slot in self._slots and len(self._slots) > 8:
+        if prefetch and slot in self._slots and len(self._slots) > 8:
             # a live track's history is wanted: fetch every live track's at once, the callers that walk parents
             # (helpFunctions.backtrackMeasurementNumbers, plotting) go over all tracks
             self._prefetch_histories()
