@@ -327,10 +327,9 @@ __device__ __forceinline__ void du_rows_body(ColView c, AssocWork w) {
 
 __global__ void du_rows_kernel(ColView c, AssocWork w) { du_rows_body(c, w); }
 
-// trees first, first + stride, ...: the whole grid (first = global thread id) or one CTA (first = threadIdx.x)
-__device__ __forceinline__ void du_decide_range(ColView c, AssocWork w, int first, int stride) {
+__device__ __forceinline__ void du_decide_body(ColView c, AssocWork w) {
     if (du_skip(c, w)) return;
-    for (int t = first; t < c.n_trees; t += stride) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
         if (w.tstart[t] < 0 || w.uf[t] != t) continue;
         w.cl_flag[t] = 0;   // flags live from here to the end of the apply phase (only roots ever carry one)
         if (w.cl_done[t]) continue;
@@ -365,9 +364,6 @@ __device__ __forceinline__ void du_decide_range(ColView c, AssocWork w, int firs
             atomicAdd(&w.stall_ctr[1], 1);
         }
     }
-}
-__device__ __forceinline__ void du_decide_body(ColView c, AssocWork w) {
-    du_decide_range(c, w, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 __global__ void du_decide_kernel(ColView c, AssocWork w) { du_decide_body(c, w); }
 
@@ -699,14 +695,14 @@ __global__ void __launch_bounds__(256) dual_loop_persistent_kernel(ColView c, As
 //   * every CTA keeps its slice of the iterated columns {cost, tree, rows} resident in shared memory for the whole
 //     launch (the column set is fixed between pricing passes), so the reduced-cost pass is shared-memory reads +
 //     ONE hop to the multipliers, and the argmin pass needs no column data at all;
-//   * the row phases (subgradient + norms, per-cluster decision, step) run in CTA 0 alone with block barriers, so an
-//     iteration has TWO cluster-wide barriers (after the tree sums, after the step) instead of five.
+//   * every thread keeps the (row, cluster) pairs it owns in registers, so the row phases are one hop as well.
 // Same arithmetic, same fixed-point sums: the result is bit-identical to the grid version.  The kernel declines
 // (info[kAssocInfo - 1] bit 30 stays clear -> the grid version runs) when the slice does not fit.
 // ------------------------------------------------------------------------------------------------
 __device__ unsigned long long g_loop_prof[16];   // ns per phase of the cluster loop (MHT_LOOP_PROF=1 prints them)
 constexpr int kClusterCtas = 16;
 constexpr int kClusterThreads = 1024;
+constexpr int kClusterRowsPerThread = 6;    // rows with a multiplier: <= 16 * 1024 * 6
 constexpr int kClusterTreesPerCta = 2048;   // span of tree ids one CTA's slice may cover
 
 __host__ __device__ inline size_t cluster_slice_bytes(int nc, int W) {
@@ -737,7 +733,7 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
     const int gtid = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     const int per = (n + nctas - 1) / nctas;
     // uniform over the cluster: every CTA sees the same n / nr
-    if (per > nc_cap) {
+    if (per > nc_cap || nr > nth * kClusterRowsPerThread || c.n_trees > nth) {
         if (gtid == 0) *declined = 1;
         return;
     }
@@ -770,10 +766,19 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
         s_cost[k] = col_cost(c, j, t);
         for (int q = 0; q < c.width; ++q) s_rows[q * nc_cap + k] = c.rows[(long long)q * c.stride + j];
     }
-    // cluster label of every listed row (never changes during the launch): the row phases below run in CTA 0 and
-    // stream row_list / row_cl instead of chasing row_owner -> uf
-    int *row_cl = w.row_holder;                // [R] scratch until the local search re-initialises it
-    for (int i = gtid; i < nr; i += nth) row_cl[i] = w.uf[w.row_owner[w.row_list[i]]];
+    // rows this thread owns for the whole launch: (row, cluster label); the label of a row never changes
+    int my_r[kClusterRowsPerThread], my_cl[kClusterRowsPerThread];
+    const int nq = (nr + nth - 1) / nth;
+#pragma unroll
+    for (int q = 0; q < kClusterRowsPerThread; ++q) {
+        const int i = gtid + q * nth;
+        my_r[q] = -1;
+        my_cl[q] = 0;
+        if (q < nq && i < nr) {
+            my_r[q] = w.row_list[i];
+            my_cl[q] = w.uf[w.row_owner[my_r[q]]];
+        }
+    }
     __syncthreads();
     const int nc_round = (nc + 31) & ~31;
     unsigned long long tp = 0;
@@ -785,26 +790,9 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
         tp = now_;                                                    \
     }
     if (gtid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tp));
-    // what the previous iteration decided, applied to THIS CTA's trees: selection of a solved cluster, done flags
-    auto settle_trees = [&]() {
-        for (int tl = threadIdx.x; tl < ntl; tl += blockDim.x) {
-            const int t = t_first + tl;
-            if (w.tstart[t] < 0) continue;
-            const int cl = w.uf[t];
-            if (w.cl_flag[cl] & 2) w.sel[t] = w.targ[t];
-            w.tdone[t] = w.cl_done[cl];
-        }
-    };
-    bool pending = false;                      // an iteration whose per-tree consequences are not applied yet
     for (int it = 0; it < iters; ++it) {
         if (((volatile int *)w.info)[0]) break;  // uniform: written before the last cluster barrier
-        if (pending) {
-            settle_trees();
-            pending = false;
-            __syncthreads();                   // phase A of this CTA reads the flags it just wrote
-        }
         if (it % greedy_every == 0) {
-            cluster.sync();                    // the greedy bodies read every tree's done flag, not only this CTA's
             dual_rc_body<false>(c, w);
             cluster.sync();
             for (int mode = 0; mode < (it ? 2 : 1); ++mode) {
@@ -889,76 +877,72 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
         }
         cluster.sync();
         LOOP_PROF(3)
-        // ---- phase B, CTA 0 alone: row subgradient + norms, per-cluster decision, step, reset -- three block-local
-        //      steps instead of three cluster-wide phases (each of those costs a MEMBAR.ALL.GPU barrier, ~2.8 us) ----
-        if (blockIdx.x == 0) {
-            const bool skip = du_skip(c, w);
-            if (!skip) {
-                for (int base = 0; base < nr; base += blockDim.x) {
-                    const int i = base + threadIdx.x;
-                    int cl = 0, g = 0;
-                    long long uf = 0;
-                    bool active = i < nr;
+        // ---- rows: subgradient, norms (this thread's rows) ----
+        if (!du_skip(c, w)) {
+#pragma unroll
+            for (int q = 0; q < kClusterRowsPerThread; ++q) {
+                if (q >= nq) break;                       // uniform
+                const int r = my_r[q], cl = my_cl[q];
+                int g = 0;
+                long long uf = 0;
+                bool active = r >= 0;
+                if (active) {
+                    active = !w.cl_done[cl];
                     if (active) {
-                        const int r = w.row_list[i];
-                        cl = row_cl[i];
-                        active = !w.cl_done[cl];
-                        if (active) {
-                            g = w.usage[r] - 1;
-                            const double ur = w.u[r];
-                            if (ur <= 0.0 && g < 0) g = 0;
-                            w.usage[r] = g;
-                            if (ur > 0.0) uf = to_fix(ur);
-                        }
+                        g = w.usage[r] - 1;
+                        const double ur = w.u[r];
+                        if (ur <= 0.0 && g < 0) g = 0;
+                        w.usage[r] = g;
+                        if (ur > 0.0) uf = to_fix(ur);
                     }
-                    warp_add_i(w.cl_nrm, cl, g * g, active);
-                    warp_add_ll(w.cl_u, cl, uf, active);
                 }
-            }
-            __syncthreads();
-            LOOP_PROF(4)
-            du_decide_range(c, w, (int)threadIdx.x, (int)blockDim.x);
-            __syncthreads();
-            LOOP_PROF(5)
-            if (c.idx && w.act_n[2]) {
-                if (threadIdx.x == 0) w.info[0] = 1;
-            } else {
-                for (int i = threadIdx.x; i < nr; i += blockDim.x) {
-                    const int r = w.row_list[i], cl = row_cl[i];
-                    const int fl = w.cl_flag[cl];
-                    const double ur = w.u[r];
-                    if (fl & 1) w.best_u[r] = ur;
-                    if (!w.cl_done[cl]) w.u[r] = fmax(0.0, ur + w.cl_step[cl] * (double)w.usage[r]);
-                    w.usage[r] = 0;
-                }
-                for (int t = threadIdx.x; t < c.n_trees; t += blockDim.x) {
-                    w.cl_m[t] = 0;
-                    w.cl_u[t] = 0;
-                    w.cl_cost[t] = 0;
-                    w.cl_nrm[t] = 0;
-                }
-                if (threadIdx.x == 0) {
-                    w.info[1] += 1;
-                    w.stall_ctr[0] = w.stall_ctr[2] ? 0 : w.stall_ctr[0] + 1;
-                    if (w.stall_ctr[1] == 0 || w.stall_ctr[0] >= kStallStop) w.info[0] = 1;
-                    w.stall_ctr[1] = 0;
-                    w.stall_ctr[2] = 0;
-                }
+                warp_add_i(w.cl_nrm, cl, g * g, active);
+                warp_add_ll(w.cl_u, cl, uf, active);
             }
         }
-        pending = true;
+        cluster.sync();
+        LOOP_PROF(4)
+        du_decide_body(c, w);
+        cluster.sync();
+        LOOP_PROF(5)
+        // ---- apply the step (this thread's rows), per-tree reset, bookkeeping ----
+        if (c.idx && w.act_n[2]) {
+            if (gtid == 0) w.info[0] = 1;
+        } else {
+#pragma unroll
+            for (int q = 0; q < kClusterRowsPerThread; ++q) {
+                if (q >= nq) break;
+                const int r = my_r[q], cl = my_cl[q];
+                if (r < 0) continue;
+                const int fl = w.cl_flag[cl];
+                const double ur = w.u[r];
+                if (fl & 1) w.best_u[r] = ur;
+                if (!w.cl_done[cl]) w.u[r] = fmax(0.0, ur + w.cl_step[cl] * (double)w.usage[r]);
+                w.usage[r] = 0;
+            }
+            for (int t = gtid; t < c.n_trees; t += nth) {
+                w.cl_m[t] = 0;
+                w.cl_u[t] = 0;
+                w.cl_cost[t] = 0;
+                w.cl_nrm[t] = 0;
+                if (w.tstart[t] < 0) continue;
+                const int cl = w.uf[t];
+                if (w.cl_flag[cl] & 2) w.sel[t] = w.targ[t];
+                w.tdone[t] = w.cl_done[cl];
+                w.tmin[t] = kKeyInf;
+                w.targ[t] = -1;
+            }
+            if (gtid == 0) {
+                w.info[1] += 1;
+                w.stall_ctr[0] = w.stall_ctr[2] ? 0 : w.stall_ctr[0] + 1;
+                if (w.stall_ctr[1] == 0 || w.stall_ctr[0] >= kStallStop) w.info[0] = 1;
+                w.stall_ctr[1] = 0;
+                w.stall_ctr[2] = 0;
+            }
+        }
         cluster.sync();
         LOOP_PROF(6)
         if (gtid == 0) g_loop_prof[7] += 1;
-    }
-    if (pending) {                              // consequences of the last iteration
-        settle_trees();
-        // per-tree scratch the later kernels expect clean
-        for (int tl = threadIdx.x; tl < ntl; tl += blockDim.x) {
-            const int t = t_first + tl;
-            w.tmin[t] = kKeyInf;
-            w.targ[t] = -1;
-        }
     }
 #undef LOOP_PROF
 }
@@ -2472,9 +2456,9 @@ static void print_loop_prof() {
     unsigned long long h[16];
     if (cudaMemcpyFromSymbol(h, g_loop_prof, sizeof(h)) != cudaSuccess) return;
     const double it = h[7] ? (double)h[7] : 1.0;
-    fprintf(stderr, "[mht] cluster loop, %.0f iterations: us/iteration greedy %.2f | phase A: min+argmin %.2f, tree sums + "
-            "barrier %.2f | phase B (CTA 0): rows %.2f, decide %.2f, apply + barrier %.2f\n", it, h[0] / it * 1e-3,
-            h[1] / it * 1e-3, h[3] / it * 1e-3, h[4] / it * 1e-3, h[5] / it * 1e-3, h[6] / it * 1e-3);
+    fprintf(stderr, "[mht] cluster loop, %.0f iterations: us/iteration greedy %.2f min+argmin %.2f trees %.2f rows %.2f "
+            "decide %.2f apply %.2f\n", it, h[0] / it * 1e-3, h[1] / it * 1e-3, h[3] / it * 1e-3, h[4] / it * 1e-3,
+            h[5] / it * 1e-3, h[6] / it * 1e-3);
 }
 
 static int dual_loop(const ColView &c, AssocWork &w, int iters, int grid_dim, cudaStream_t s) {
