@@ -93,10 +93,29 @@ def meas_capacity(name):
     return 8192 if need <= 8192 else 1 << int(np.ceil(np.log2(need)))
 
 
-def make_tracker(name):
+def capacities(name, n_scans):
+    """(maxNodes, maxParents): the steady-state sizes of the table, or what a short cold-start run needs (the forest
+    grows ~x5 per scan from nT leaves until the window fills)."""
+    nT, _, _, N, _, _, max_nodes, max_par = WORKLOADS[name]
+    if n_scans <= N:
+        need = int(nT * 3.2 * 5.8 ** max(n_scans - 1, 0) * 1.3)
+        return min(max_nodes, max(1 << 22, need)), min(max_par, max(1 << 20, need // 3))
+    return max_nodes, max_par
+
+
+def metric_name(name):
+    nT, R, lam = WORKLOADS[name][:3]
+    if name.startswith("cfg3"):
+        return "scans/sec @ 1k targets, 5k meas/scan"
+    return "scans/sec @ %dk targets, %dk meas/scan" % (nT // 1000, int(round((nT * 0.9 + lam * np.pi * R * R) / 1000.0))) \
+        if nT >= 1000 else "scans/sec @ %d targets, %d meas/scan" % (nT, int(nT * 0.9 + lam * np.pi * R * R))
+
+
+def make_tracker(name, n_scans=1 << 30):
     from pymht_b200.tracker import Tracker
     from pymht_b200.models import pv
     nT, R, lam, N, Pd, seed, max_nodes, max_par = WORKLOADS[name]
+    max_nodes, max_par = capacities(name, n_scans)
     trk = Tracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=meas_capacity(name),
                   maxNodes=max_nodes, maxParents=max_par,
                   maxDualIterations=int(os.environ.get("MHT_DUAL_ITERS", "120")))
@@ -146,7 +165,7 @@ def run_device_leg(name, scans, simList, preroll, warmup, steps):
     """Timed with the library's CUDA events (first kernel -> results on host), scans resident in HBM."""
     import torch
     from pymht_b200 import _lib
-    trk = make_tracker(name)
+    trk = make_tracker(name, len(scans))
     trk.preInitialize(simList)
     lib = trk._lib
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -169,7 +188,7 @@ def run_device_leg(name, scans, simList, preroll, warmup, steps):
 
 
 def run_e2e_leg(name, scans, simList, preroll, warmup, steps):
-    trk = make_tracker(name)
+    trk = make_tracker(name, len(scans))
     trk.preInitialize(simList)
     t_steps = []
     for k, s in enumerate(scans):
@@ -257,6 +276,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3_1k_targets_5k_meas_N6", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--preroll", type=int, default=-1,
+                    help="untimed scans before the warm-up (default N+2 = the window is full); 0 = time the cold start")
     ap.add_argument("--shard", default="sectors", choices=["sectors", "trees"],
                     help="N>1: 'sectors' = one independent region per rank (weak scaling, default); 'trees' = the "
                          "trees of ONE region sharded over the ranks, column records all-gathered (strong scaling)")
@@ -266,9 +287,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     name = args.workload
     nT, R, lam, N, Pd, seed, _, _ = WORKLOADS[name]
-    if name.startswith("cfg4") and not (args.shard == "trees" and world > 1):
+    preroll = N + 2 if args.preroll < 0 else args.preroll
+    if name.startswith("cfg4") and not (args.shard == "trees" and world > 1) and preroll + args.warmup + args.steps > 5:
         raise SystemExit("cfg4 (10k targets) exceeds one GPU's HBM while the window fills: run it with --shard trees "
-                         "under torchrun on 8 GPUs")
+                         "under torchrun on 8 GPUs, or time the cold start (--preroll 0 --warmup 1 --steps 4)")
     config = {"workload": name, "targets": nT, "meas_per_scan": "~%d" % int(nT * Pd + lam * np.pi * R * R),
               "lambda_phi": lam, "n_scan": N, "P_d": Pd, "model": "CV (pv)", "radar_period_s": T_RADAR,
               "l2": "per-scan working set (hypothesis levels, GBs) exceeds the 126 MB L2; no explicit flush",
@@ -277,10 +299,10 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        kind, times, leaves = run_cpu_reference(name, max_scans=2, n_scans_scenario=N + 2 + args.warmup + args.steps)
+        kind, times, leaves = run_cpu_reference(name, max_scans=2, n_scans_scenario=preroll + args.warmup + args.steps)
         v = len(times) / sum(times)
         config["scans"] = SCENARIO_SOURCE
-        line = {"metric": "scans/sec @ 1k targets, 5k meas/scan", "value": v, "unit": "scans/s", "n_gpus": args.gpus,
+        line = {"metric": metric_name(name), "value": v, "unit": "scans/s", "n_gpus": args.gpus,
                 "steps": len(times), "warmup": 0, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64 state / f32 covariance", "data": "synthetic", "config": config,
                 "impl": "reference",
@@ -301,8 +323,8 @@ def main():
         # carries exactly one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    preroll = N + 2
     n_scans = preroll + args.warmup + args.steps
+    config["preroll_scans"] = preroll
     if args.shard == "trees" and world > 1:
         return run_tree_sharded(args, name, config, dist, torch, rank, world, local_rank, preroll, n_scans)
     simList, scans = make_scenario(name, n_scans, seed_offset=rank)
@@ -375,7 +397,7 @@ def main():
         ilp_ach = it_bytes / (us_iter * 1e-6) / 1e9 if us_iter > 0 else 0.0
         gaps = [d["objective"] - d["lower_bound"] for d in timed]
         line = {
-            "metric": "scans/sec @ 1k targets, 5k meas/scan", "value": value, "unit": "scans/s", "n_gpus": world,
+            "metric": metric_name(name), "value": value, "unit": "scans/s", "n_gpus": world,
             "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 state / f32 covariance", "data": "synthetic",
             "config": config,
@@ -442,6 +464,7 @@ def run_tree_sharded(args, name, config, dist, torch, rank, world, local_rank, p
     from pymht_b200.tracker import Tracker
     from pymht_b200.models import pv
     nT, R, lam, N, Pd, seed, max_nodes, max_par = WORKLOADS[name]
+    max_nodes, max_par = capacities(name, n_scans)
     simList, scans = make_scenario(name, n_scans, seed_offset=0)      # the same region on every rank
     dev = torch.device("cuda", local_rank)
     mcap = meas_capacity(name)
@@ -494,7 +517,7 @@ def run_tree_sharded(args, name, config, dist, torch, rank, world, local_rank, p
         config = dict(config, scans=SCENARIO_SOURCE,
                       parallelism="trees of one region sharded over %d GPUs; ONE all-gather of packed %d-byte column "
                       "records per scan (NCCL) + replicated, warm-started global solve" % (world, log[-1]["record_bytes"]))
-        line = {"metric": "scans/sec @ 1k targets, 5k meas/scan", "value": v, "unit": "scans/s", "n_gpus": world,
+        line = {"metric": metric_name(name), "value": v, "unit": "scans/s", "n_gpus": world,
                 "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64 state / f32 covariance", "data": "synthetic", "config": config,
                 "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": int(np.mean([16 * len(s.measurements) for s in scans])),

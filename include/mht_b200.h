@@ -142,7 +142,7 @@ typedef struct mht_forest_config {
     int32_t max_dual_iters;  /* Lagrangian iterations per scan        */
     int32_t exact_ms;        /* wall-clock budget (ms) per scan of the exact branch & bound that closes the
                                 components the dual loop leaves open (tracker.py:1155-1217 is an exact MILP);
-                                0 = default (10 ms), < 0 = no exact search.  A scan whose budget ran out returns
+                                0 = default (8 ms), < 0 = no exact search.  A scan whose budget ran out returns
                                 a feasible selection with certified = 0 and the bound gap in mht_scan_info. */
 } mht_forest_config;
 

@@ -1225,7 +1225,7 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
         return MHT_OK;
     }
     if (phase == 0) {
-        const double exact_ms = f->cfg.exact_ms == 0 ? 10.0 : (f->cfg.exact_ms < 0 ? 0.0 : (double)f->cfg.exact_ms);
+        const double exact_ms = f->cfg.exact_ms == 0 ? 8.0 : (f->cfg.exact_ms < 0 ? 0.0 : (double)f->cfg.exact_ms);
         AssocEvents aev;
         aev.after_cluster = f->ev[5];
         for (int i = 0; i < 8; ++i) aev.dual[i] = f->evx[i];
