@@ -98,8 +98,8 @@ def capacities(name, n_scans):
     grows ~x5 per scan from nT leaves until the window fills)."""
     nT, _, _, N, _, _, max_nodes, max_par = WORKLOADS[name]
     if n_scans <= N:
-        need = int(nT * 3.2 * 5.8 ** max(n_scans - 1, 0) * 1.3)
-        return min(max_nodes, max(1 << 22, need)), min(max_par, max(1 << 20, need // 3))
+        need = int(nT * 3.2 * 5.8 ** max(n_scans - 1, 0) * 2.0)
+        return min(max_nodes, max(1 << 22, need)), min(max_par, max(1 << 20, need // 2))
     return max_nodes, max_par
 
 

@@ -6,4 +6,4 @@ d=json.load(open('gpurun_out/bench_r2_cfg4_n1.json'))
 for k in ('metric','value','e2e','stage_ms','scan_ms','ilp','roofline'):
     print(k, d.get(k))
 PY
-timeout 1500 python -m pytest tests -q -m gpu -x -s 2>&1 | grep -E "cfg3_scan3|NOT CERT|^E |passed|failed|Error" | cut -c1-500 | head -20
+
