@@ -98,7 +98,7 @@ def capacities(name, n_scans):
     grows ~x5 per scan from nT leaves until the window fills)."""
     nT, _, _, N, _, _, max_nodes, max_par = WORKLOADS[name]
     if n_scans <= N:
-        need = int(nT * 3.2 * 5.8 ** max(n_scans - 1, 0) * 2.0)
+        need = int(nT * 3.2 * 7.5 ** max(n_scans - 1, 0) * 2.0)   # x5-7 per scan (the 10k-target scene is denser at its centre)
         return min(max_nodes, max(1 << 22, need)), min(max_par, max(1 << 20, need // 2))
     return max_nodes, max_par
 
@@ -288,9 +288,9 @@ def main():
     name = args.workload
     nT, R, lam, N, Pd, seed, _, _ = WORKLOADS[name]
     preroll = N + 2 if args.preroll < 0 else args.preroll
-    if name.startswith("cfg4") and not (args.shard == "trees" and world > 1) and preroll + args.warmup + args.steps > 5:
+    if name.startswith("cfg4") and not (args.shard == "trees" and world > 1) and preroll + args.warmup + args.steps > 4:
         raise SystemExit("cfg4 (10k targets) exceeds one GPU's HBM while the window fills: run it with --shard trees "
-                         "under torchrun on 8 GPUs, or time the cold start (--preroll 0 --warmup 1 --steps 4)")
+                         "under torchrun on 8 GPUs, or time the cold start (--preroll 0 --warmup 1 --steps 3)")
     config = {"workload": name, "targets": nT, "meas_per_scan": "~%d" % int(nT * Pd + lam * np.pi * R * R),
               "lambda_phi": lam, "n_scan": N, "P_d": Pd, "model": "CV (pv)", "radar_period_s": T_RADAR,
               "l2": "per-scan working set (hypothesis levels, GBs) exceeds the 126 MB L2; no explicit flush",
