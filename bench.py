@@ -469,26 +469,31 @@ def run_tree_sharded(args, name, config, dist, torch, rank, world, local_rank, p
     dev = torch.device("cuda", local_rank)
     mcap = meas_capacity(name)
 
-    # ---- parity leg: scans 1-2 (certified on both sides), sharded vs single forest ----
+    # ---- parity leg: the first scans, sharded vs single forest.  A certified solve is the unique optimum on both sides;
+    #      an uncertified one depends on which worker found which incumbent first, so only scans certified on BOTH
+    #      sides are compared (and the tracks a later scan inherits are only comparable while that holds) ----
     n_verify = 2
     vt = ShardedTracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=mcap,
                         maxNodes=1 << 22, maxParents=1 << 20, exactBudgetMs=10000)
     vt.mergeThreshold = 0.0
     vt.preInitialize(simList)
+    v_sharded = []
     for s in scans[:n_verify]:
         vt.addMeasurementList(s)
-    v_sharded = tracks_digest(vt.gatherTracks())
+        v_sharded.append(tracks_digest(vt.gatherTracks()))
     v_cert = [int(d["certified"]) for d in vt.scanInfo]
     vt.close()
-    v_single = None
+    v_single, v_cert1 = None, None
     if rank == 0:
         st = Tracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=mcap,
                      maxNodes=1 << 22, maxParents=1 << 20, exactBudgetMs=10000)
         st.mergeThreshold = 0.0
         st.preInitialize(simList)
+        v_single = []
         for s in scans[:n_verify]:
             st.addMeasurementList(s)
-        v_single = tracks_digest([(n.ID, n.measurementNumber, n.cumulativeNLLR) for n in st.getTrackNodes()])
+            v_single.append(tracks_digest([(n.ID, n.measurementNumber, n.cumulativeNLLR) for n in st.getTrackNodes()]))
+        v_cert1 = [int(d["certified"]) for d in st.scanInfo]
         st.close()
 
     per = 1.0 / world + 0.15
@@ -535,11 +540,23 @@ def run_tree_sharded(args, name, config, dist, torch, rank, world, local_rank, p
                                "certified": float(np.mean([d["certified"] for d in infos])),
                                "objective": float(np.mean([d["objective"] for d in infos])),
                                "lower_bound": float(np.mean([d["lower_bound"] for d in infos]))},
-                "parity": {"scans": n_verify, "sharded_hash": v_sharded, "single_forest_hash": v_single,
-                           "equal": v_sharded == v_single, "certified": v_cert}}
+                "parity": parity_summary(v_sharded, v_single, v_cert, v_cert1)}
         emit(line)
     trk.close()
     dist.destroy_process_group()
+
+
+def parity_summary(h_sharded, h_single, cert_sharded, cert_single):
+    """Per-scan digests of the sharded and the single-forest run; `equal` covers the leading scans certified on both
+    sides (at least one must be)."""
+    n_cmp = 0
+    for a, b in zip(cert_sharded, cert_single):
+        if not (a and b):
+            break
+        n_cmp += 1
+    return {"scans": len(h_sharded), "sharded_hash": h_sharded, "single_forest_hash": h_single,
+            "certified_sharded": cert_sharded, "certified_single": cert_single, "scans_compared": n_cmp,
+            "equal": bool(n_cmp > 0 and h_sharded[:n_cmp] == h_single[:n_cmp])}
 
 
 def exchange(dist, device, t_dev, t_e2e, n_tracks):
