@@ -118,7 +118,8 @@ int mht_assoc_solve(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t wid
 int mht_assoc_solve_warm(int64_t n_cols, int64_t cap_cols, int64_t n_trees, int64_t n_rows, int32_t width,
                          const double *d_col_cost, const int32_t *d_col_tree, const int32_t *d_col_rows,
                          int32_t *d_selected_col, double *h_info, void *d_work, void *stream, int32_t warm,
-                         int64_t clear_row_lo, int64_t clear_row_hi, double exact_ms /* <= 0: default 10 s */);
+                         int64_t clear_row_lo, int64_t clear_row_hi, double exact_ms /* <= 0: default 10 s */,
+                         int32_t max_dual_iters /* per sifting round; <= 0: default 200 */);
 
 /* ------------------------------------------------------------------------------------------------
  * Device-resident hypothesis forest: steps 1-3 + terminate + N-scan prune of

@@ -68,7 +68,7 @@ _SIGNATURES = {
     "mht_assoc_workspace": (_i64, [_i64, _i64, _i64, _i32]),
     "mht_cluster": (C.c_int, [_i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mht_assoc_solve": (C.c_int, [_i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "mht_assoc_solve_warm": (C.c_int, [_i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _dbl]),
+    "mht_assoc_solve_warm": (C.c_int, [_i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _dbl, _i32]),
     "mht_record_bytes": (_i32, [_i32]),
     "mht_forest_export_records": (C.c_int, [_vp, _i32, _vp, _i64]),
     "mht_unpack_records": (C.c_int, [_i32, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),

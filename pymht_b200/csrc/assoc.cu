@@ -2693,7 +2693,7 @@ extern "C" int mht_cluster(int64_t n_cols, int64_t n_trees, int64_t n_rows, int3
 static int assoc_solve_entry(int64_t n_cols, int64_t n_trees, int64_t n_rows, int32_t width, const double *d_col_cost,
                              const int32_t *d_col_tree, const int32_t *d_col_rows, int32_t *d_selected_col, double *h_info,
                              void *d_work, void *stream, bool warm, int64_t clear_lo, int64_t clear_hi,
-                             int64_t cap_cols = -1, double exact_ms = 10000.0) {
+                             int64_t cap_cols = -1, double exact_ms = 10000.0, int max_iters = 200) {
     if (int rc = check_device()) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     ColView c;
@@ -2702,7 +2702,8 @@ static int assoc_solve_entry(int64_t n_cols, int64_t n_trees, int64_t n_rows, in
         return rc;
     if (warm && clear_hi > clear_lo && clear_lo >= 0 && clear_hi <= n_rows)
         MHT_CUDA(cudaMemsetAsync(w.u + clear_lo, 0, sizeof(double) * (size_t)(clear_hi - clear_lo), s));
-    if (int rc = assoc_solve(c, w, 200, 4096, kSMs * 4, s, nullptr, warm, n_cols > 2000000, false, exact_ms)) return rc;
+    // sifting (iterate on an active column list) from 10^6 columns on, like the forest
+    if (int rc = assoc_solve(c, w, max_iters, 4096, kSMs * 8, s, nullptr, warm, n_cols > 1000000, false, exact_ms)) return rc;
     MHT_CUDA(cudaMemcpyAsync(d_selected_col, w.sel, n_trees * sizeof(int), cudaMemcpyDeviceToDevice, s));
     int info[kAssocInfo];
     double obj[2];
@@ -2738,8 +2739,8 @@ extern "C" int mht_assoc_solve(int64_t n_cols, int64_t n_trees, int64_t n_rows, 
 extern "C" int mht_assoc_solve_warm(int64_t n_cols, int64_t cap_cols, int64_t n_trees, int64_t n_rows, int32_t width,
                                     const double *d_col_cost, const int32_t *d_col_tree, const int32_t *d_col_rows,
                                     int32_t *d_selected_col, double *h_info, void *d_work, void *stream, int32_t warm,
-                                    int64_t clear_row_lo, int64_t clear_row_hi, double exact_ms) {
+                                    int64_t clear_row_lo, int64_t clear_row_hi, double exact_ms, int32_t max_dual_iters) {
     return assoc_solve_entry(n_cols, n_trees, n_rows, width, d_col_cost, d_col_tree, d_col_rows, d_selected_col, h_info,
                              d_work, stream, warm != 0, clear_row_lo, clear_row_hi, cap_cols,
-                             exact_ms > 0.0 ? exact_ms : 10000.0);
+                             exact_ms > 0.0 ? exact_ms : 10000.0, max_dual_iters > 0 ? max_dual_iters : 200);
 }

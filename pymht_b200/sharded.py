@@ -183,7 +183,7 @@ class ShardedTracker(Tracker):
             _lib.check(lib.mht_assoc_solve_warm(n_total, cap, t_total_slots, n_rows, W, cost.data_ptr(), tree.data_ptr(),
                                                 rows.data_ptr(), sel.data_ptr(), _lib.ptr(ext), work.data_ptr(), None,
                                                 warm, plane * self.maxMeasurements, (plane + 1) * self.maxMeasurements,
-                                                float(self.exactBudgetMs if self.exactBudgetMs > 0 else 10.0)),
+                                                float(self.exactBudgetMs if self.exactBudgetMs > 0 else 8.0), int(self.maxDualIterations)),
                        allow=(_lib.MHT_E_NOTOPTIMAL,))
             dist.broadcast(sel, src=0, group=self._group)     # one global hypothesis for every shard
             torch.cuda.current_stream().synchronize()
