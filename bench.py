@@ -409,11 +409,11 @@ def main():
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "bytes_per_launch": bytes_gate, "ms_per_launch": ms_gate},
-            "roofline_ilp": {"bound": "hbm", "kernel": "dual_loop_persistent_kernel (one projected-subgradient iteration)",
+            "roofline_ilp": {"bound": "hbm", "kernel": "dual_loop_cluster_kernel (one projected-subgradient iteration; grid fallback dual_loop_persistent_kernel)",
                              "bytes_per_iteration": it_bytes, "us_per_iteration": us_iter, "iterations_per_scan": iters,
                              "ms_dual_per_scan": ms_dual, "achieved": ilp_ach, "peak": peak, "unit": "GB/s",
                              "frac": ilp_ach / peak,
-                             "note": "latency bound (grid barriers), far from HBM: the iteration's working set is L2 resident"},
+                             "note": "latency bound (dependent L2 round trips + atomics per cluster-wide phase, profiles/cluster_barrier_cost_r2.txt), far from HBM: the iteration's working set is L2 / shared-memory resident"},
             "stage_ms": {k: float(np.mean([d[k] for d in timed])) for k in
                          ("ms_gate", "ms_cluster", "ms_assoc", "ms_dual", "ms_exact", "ms_prune", "ms_total")},
             "scan_ms": {"ms_total": pct("ms_total"), "ms_assoc": pct("ms_assoc"), "ms_gate": pct("ms_gate")},
