@@ -327,42 +327,47 @@ __device__ __forceinline__ void du_rows_body(ColView c, AssocWork w) {
 
 __global__ void du_rows_kernel(ColView c, AssocWork w) { du_rows_body(c, w); }
 
+// the decision of ONE cluster (t = its root, a tree that has columns)
+__device__ __forceinline__ void du_decide_one(const AssocWork &w, int t) {
+    w.cl_flag[t] = 0;   // flags live from here to the end of the apply phase (only roots ever carry one)
+    if (w.cl_done[t]) return;
+    const double L = from_fix(w.cl_m[t] - w.cl_u[t]);
+    const int nrm = w.cl_nrm[t];
+    if (nrm == 0) {  // conflict-free and complementary: argmins are optimal
+        w.cl_done[t] = 1;
+        w.cl_best[t] = L;
+        w.cl_ub[t] = from_fix(w.cl_cost[t]);
+        w.cl_flag[t] = 3;
+        w.cl_step[t] = 0.0;
+        atomicOr(&w.stall_ctr[2], 1);
+        return;
+    }
+    if (L > w.cl_best[t] + 1e-12) {
+        // flag 1 = keep these multipliers; flag 8 = the gain is large enough to keep iterating
+        const bool big = L > w.cl_best[t] + kBigGain * fmax(1.0, fabs(L));
+        w.cl_flag[t] = big ? 9 : 1;
+        if (big) atomicOr(&w.stall_ctr[2], 1);
+        w.cl_best[t] = L;
+        w.cl_stall[t] = 0;
+    } else if (++w.cl_stall[t] >= kPatience) {
+        w.cl_theta[t] *= kShrink;
+        w.cl_stall[t] = 0;
+    }
+    if (w.cl_ub[t] - w.cl_best[t] < 1e-9) {
+        w.cl_done[t] = 1;
+        w.cl_step[t] = 0.0;
+    } else {
+        // no step before the first primal solution provides an upper bound
+        w.cl_step[t] = w.cl_ub[t] < 1e299 ? w.cl_theta[t] * (w.cl_ub[t] - L) / (double)nrm : 0.0;
+        atomicAdd(&w.stall_ctr[1], 1);
+    }
+}
+
 __device__ __forceinline__ void du_decide_body(ColView c, AssocWork w) {
     if (du_skip(c, w)) return;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
         if (w.tstart[t] < 0 || w.uf[t] != t) continue;
-        w.cl_flag[t] = 0;   // flags live from here to the end of the apply phase (only roots ever carry one)
-        if (w.cl_done[t]) continue;
-        const double L = from_fix(w.cl_m[t] - w.cl_u[t]);
-        const int nrm = w.cl_nrm[t];
-        if (nrm == 0) {  // conflict-free and complementary: argmins are optimal
-            w.cl_done[t] = 1;
-            w.cl_best[t] = L;
-            w.cl_ub[t] = from_fix(w.cl_cost[t]);
-            w.cl_flag[t] = 3;
-            w.cl_step[t] = 0.0;
-            atomicOr(&w.stall_ctr[2], 1);
-            continue;
-        }
-        if (L > w.cl_best[t] + 1e-12) {
-            // flag 1 = keep these multipliers; flag 8 = the gain is large enough to keep iterating
-            const bool big = L > w.cl_best[t] + kBigGain * fmax(1.0, fabs(L));
-            w.cl_flag[t] = big ? 9 : 1;
-            if (big) atomicOr(&w.stall_ctr[2], 1);
-            w.cl_best[t] = L;
-            w.cl_stall[t] = 0;
-        } else if (++w.cl_stall[t] >= kPatience) {
-            w.cl_theta[t] *= kShrink;
-            w.cl_stall[t] = 0;
-        }
-        if (w.cl_ub[t] - w.cl_best[t] < 1e-9) {
-            w.cl_done[t] = 1;
-            w.cl_step[t] = 0.0;
-        } else {
-            // no step before the first primal solution provides an upper bound
-            w.cl_step[t] = w.cl_ub[t] < 1e299 ? w.cl_theta[t] * (w.cl_ub[t] - L) / (double)nrm : 0.0;
-            atomicAdd(&w.stall_ctr[1], 1);
-        }
+        du_decide_one(w, t);
     }
 }
 __global__ void du_decide_kernel(ColView c, AssocWork w) { du_decide_body(c, w); }
@@ -706,7 +711,7 @@ constexpr int kClusterRowsPerThread = 6;    // rows with a multiplier: <= 16 * 1
 constexpr int kClusterTreesPerCta = 2048;   // span of tree ids one CTA's slice may cover
 
 __host__ __device__ inline size_t cluster_slice_bytes(int nc, int W) {
-    return (size_t)nc * (8 + 8 + 4 + 4 * (size_t)W) + (size_t)kClusterTreesPerCta * 12 + 64;
+    return (size_t)nc * (8 + 8 + 4 + 4 * (size_t)W) + (size_t)kClusterTreesPerCta * 16 + 64;
 }
 
 // first position >= i of the iterated list where a new tree starts (columns are sorted by tree)
@@ -759,6 +764,7 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
     int *s_tree = (int *)(s_tmin + kClusterTreesPerCta);
     int *s_rows = s_tree + nc_cap;             // [W][nc_cap]
     int *s_targ = s_rows + (size_t)c.width * nc_cap;                     // [kClusterTreesPerCta] local column of the argmin
+    int *s_cl = s_targ + kClusterTreesPerCta;                            // [kClusterTreesPerCta] cluster label of the tree
     for (int k = threadIdx.x; k < nc; k += blockDim.x) {
         const int j = c.idx ? c.idx[lo + k] : lo + k;
         const int t = c.tree[j];
@@ -779,6 +785,18 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
             my_cl[q] = w.uf[w.row_owner[my_r[q]]];
         }
     }
+    // the tree this thread serves in the per-tree phases (the kernel declines when n_trees > nth): its cluster label
+    // and whether it has columns / is its cluster's root never change during the launch
+    const int my_t = gtid < c.n_trees ? gtid : -1;
+    int my_t_cl = 0;
+    bool my_t_has = false, my_t_root = false;
+    if (my_t >= 0) {
+        my_t_has = w.tstart[my_t] >= 0;
+        my_t_cl = w.uf[my_t];
+        my_t_root = my_t_has && my_t_cl == my_t;
+    }
+    // cluster label of the trees of this CTA's slice (phase A)
+    for (int tl = threadIdx.x; tl < ntl; tl += blockDim.x) s_cl[tl] = w.uf[t_first + tl];
     __syncthreads();
     const int nc_round = (nc + 31) & ~31;
     unsigned long long tp = 0;
@@ -860,7 +878,7 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
                 if (active) {
                     const int t = t_first + tl;
                     const int j = c.idx ? c.idx[lo + k] : lo + k;
-                    cl = w.uf[t];
+                    cl = s_cl[tl];
                     w.freq[j] += 1;  // ergodic primal estimate: how often this column is the tree's Lagrangian choice
                     w.targ[t] = j;
                     w.tmin[t] = s_tmin[tl];
@@ -902,7 +920,7 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
         }
         cluster.sync();
         LOOP_PROF(4)
-        du_decide_body(c, w);
+        if (my_t_root && !du_skip(c, w)) du_decide_one(w, my_t);
         cluster.sync();
         LOOP_PROF(5)
         // ---- apply the step (this thread's rows), per-tree reset, bookkeeping ----
@@ -920,17 +938,19 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
                 if (!w.cl_done[cl]) w.u[r] = fmax(0.0, ur + w.cl_step[cl] * (double)w.usage[r]);
                 w.usage[r] = 0;
             }
-            for (int t = gtid; t < c.n_trees; t += nth) {
+            if (my_t >= 0) {
+                const int t = my_t;
                 w.cl_m[t] = 0;
                 w.cl_u[t] = 0;
                 w.cl_cost[t] = 0;
                 w.cl_nrm[t] = 0;
-                if (w.tstart[t] < 0) continue;
-                const int cl = w.uf[t];
-                if (w.cl_flag[cl] & 2) w.sel[t] = w.targ[t];
-                w.tdone[t] = w.cl_done[cl];
-                w.tmin[t] = kKeyInf;
-                w.targ[t] = -1;
+                if (my_t_has) {
+                    const int cl = my_t_cl;
+                    if (w.cl_flag[cl] & 2) w.sel[t] = w.targ[t];
+                    w.tdone[t] = w.cl_done[cl];
+                    w.tmin[t] = kKeyInf;
+                    w.targ[t] = -1;
+                }
             }
             if (gtid == 0) {
                 w.info[1] += 1;
@@ -2419,7 +2439,7 @@ static ClusterPlan cluster_plan(int W) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const size_t budget = (size_t)optin - 2048;   // static shared memory of the greedy bodies + reserve
-    int nc_cap = (int)((budget - 64 - (size_t)kClusterTreesPerCta * 12) / (8 + 8 + 4 + 4 * (size_t)W));
+    int nc_cap = (int)((budget - 64 - (size_t)kClusterTreesPerCta * 16) / (8 + 8 + 4 + 4 * (size_t)W));
     nc_cap &= ~31;
     if (nc_cap < 256) return plans[W] = best;
     const size_t smem = cluster_slice_bytes(nc_cap, W);
