@@ -1805,7 +1805,7 @@ __global__ void __launch_bounds__(32) branch_bound_kernel(ColView c, AssocWork w
 // node evaluation, every CTA of the grid serving one shared node pool
 // ------------------------------------------------------------------------------------------------
 // single CTA: which components still need the search, offsets of their compacted cores
-__global__ void __launch_bounds__(1024, 1) bb_plan_kernel(ColView c, AssocWork w, int max_cols_now) {
+__global__ void __launch_bounds__(1024, 1) bb_plan_kernel(ColView c, AssocWork w, int max_cols_now, double max_gap_now) {
     BBWork &b = w.bbw;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 16; ++i) b.hdr[i] = 0;
@@ -1830,6 +1830,9 @@ __global__ void __launch_bounds__(1024, 1) bb_plan_kernel(ColView c, AssocWork w
             if (b.comp_state[k]) continue;
             const int nT = w.comp_off[k + 1] - w.comp_off[k], nC = w.cl_stall[k];
             if (nC > b.max_cols || nC > max_cols_now || nT > b.max_trees || n >= kBBMaxNodes / 4) continue;   // stays open: uncertified
+            // the effort of closing a component grows exponentially with its cluster's gap: what the time box cannot
+            // hope to close is not started (measured on the bench: nothing above a gap of 2 closes in 8 ms)
+            if (nT > kDfsMaxTrees && w.cl_step[w.uf[w.comp_trees[w.comp_off[k]]]] > max_gap_now) continue;
             bb::Comp &p = b.comps[n];
             p.nC = nC;
             p.nT = nT;
@@ -2629,7 +2632,8 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
         // a dual iteration on n columns costs ~n / 4e9 s in one CTA: components the time box cannot even evaluate
         // a few hundred times are left alone (they stay open, the scan is reported uncertified)
         const double cols_now = ms * 4000.0;
-        count_launch(), bb_plan_kernel<<<1, 1024, 0, s>>>(c, w, cols_now > 1e9 ? 1000000000 : (int)cols_now);
+        static const double gap_per_ms = getenv("MHT_BB_GAP_PER_MS") ? atof(getenv("MHT_BB_GAP_PER_MS")) : 0.125;
+        count_launch(), bb_plan_kernel<<<1, 1024, 0, s>>>(c, w, cols_now > 1e9 ? 1000000000 : (int)cols_now, 1.0 + gap_per_ms * ms);
         if (ms > 0.0) {
             count_launch(), bb_compact_kernel<<<kSMs, 256, 0, s>>>(c, w);
             count_launch(), bb_root_kernel<<<kSMs, 256, 0, s>>>(c, w, ms);
