@@ -32,6 +32,10 @@ def _scenario(name):
         return None, 10, 760.0, 1e-4, 4, 0.9, 1234, 20
     if name == "cfg2":
         return None, 8, 1702.0, 1e-4, 4, 0.9, 1234, 100
+    if name == "cfg2_long":
+        # BASELINE config 2 run well into its steady state: 30 scans (window N = 4 full from scan 5 on; N-scan pruning,
+        # terminations and re-clustering every scan) -- the longest sequence the reference replays in about a minute
+        return None, 30, 1702.0, 1e-4, 4, 0.9, 2468, 100
     if name == "cfg3_head":
         return None, 2, 1142.0, 1e-3, 6, 0.9, 1234, 1000
     if name == "cfg3_lowclutter":

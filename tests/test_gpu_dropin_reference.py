@@ -121,7 +121,7 @@ def _install_stubs(trk, calls):
     trk._solveBLP_OR_TOOLS = types.MethodType(_solveBLP_OR_TOOLS, trk)
 
 
-@pytest.mark.parametrize("name", ["cfg1_crossing", "cfg2_small", "cfg5_small"])
+@pytest.mark.parametrize("name", ["cfg1_crossing", "cfg2_small", "cfg5_small", "cfg2"])
 def test_patched_reference_reproduces_reference_tracks(name):
     g = golden(name)
     T, lam_phi, lam_nu, N, Pd, eta2, R = [float(v) for v in g["params"]]

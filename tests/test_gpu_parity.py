@@ -178,7 +178,7 @@ def _replay_tracker(name, n_scans=None, scan_kw=None, setup=None, **kw):
     trk.close()
 
 
-@pytest.mark.parametrize("name", ["cfg1_crossing", "cfg2_small", "cfg5_small", "cfg2", "cfg5_n8"])
+@pytest.mark.parametrize("name", ["cfg1_crossing", "cfg2_small", "cfg5_small", "cfg2", "cfg5_n8", "cfg2_long"])
 def test_tracker_replays_reference_golden(name):
     """Whole addMeasurementList sequences against what the unmodified reference produced."""
     for k, g, pre, trk, nodes, hist, info in _replay_tracker(name):

@@ -98,3 +98,8 @@ def test_replay_cfg5_full():
     """BASELINE config 5 at full size (500 targets, 50 scripted 90-degree crossings, N = 8): scans 1-4 (scans 5-6
     hold 3.4e4 / 8.6e4 leaves in one cluster -- minutes of HiGHS; the GPU test replays all six)."""
     replay("cfg5_full", n_scans=4)
+
+
+def test_replay_cfg2_long():
+    """BASELINE config 2 for 30 scans: 25 scans of steady state (N-scan pruning, terminations, re-clustering)."""
+    replay("cfg2_long", n_scans=30)
