@@ -264,6 +264,11 @@ int mht_forest_history(mht_forest *f, int32_t slot, int32_t cap, int32_t *n, int
 int mht_forest_histories(mht_forest *f, int32_t cap_tracks, int32_t cap_len, int32_t *n_tracks, int32_t *h_slot,
                          int32_t *h_len, int32_t *h_meas, double *h_x, double *h_cnllr, float *h_P);
 
+/* Tracker.__associatedMeasurements__[i] (tracker.py:83,331-332,1226-1227): the (scanNumber, measurementNumber) pairs of
+ * every node below the tree's current root (Target.getMeasurementSet, pyTarget.py:414-430), after the last scan's pruning.
+ * MHT_E_CAPACITY: *n holds the required count. */
+int mht_forest_measurement_set(mht_forest *f, int32_t slot, int32_t cap, int32_t *n, int32_t *h_scan, int32_t *h_meas);
+
 /* Smallest distance from (px,py) to any live leaf's position: the test of
  * Target.haveNoNeightbours (pymht/pyTarget.py:181-189) used by Tracker.initiateTarget. */
 int mht_forest_min_leaf_distance(mht_forest *f, double px, double py, double *dist);

@@ -87,6 +87,7 @@ _SIGNATURES = {
     "mht_forest_windows": (C.c_int, [_vp, _i32, C.POINTER(_i32), _vp, _vp]),
     "mht_forest_history": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i32), _vp, _vp, _vp, _vp]),
     "mht_forest_histories": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i32), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mht_forest_measurement_set": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i32), _vp, _vp]),
     "mht_forest_min_leaf_distance": (C.c_int, [_vp, _dbl, _dbl, C.POINTER(_dbl)]),
     "mht_forest_leaves": (C.c_int, [_vp, _i32, _i64, C.POINTER(_i64), _vp, _vp, _vp]),
 }

@@ -1831,6 +1831,66 @@ extern "C" int mht_forest_history(mht_forest *f, int32_t slot, int32_t cap, int3
     return MHT_OK;
 }
 
+// measurement rows on the root->leaf paths of one tree's live leaves -> bitmap (one bit per row)
+__global__ void measurement_set_kernel(const int *rows, long long stride, int W, int lo, int hi, unsigned *bits) {
+    const long long n = (long long)(hi - lo) * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(i / (hi - lo)), leaf = lo + (int)(i % (hi - lo));
+        const int r = rows[(long long)w * stride + leaf];
+        if (r >= 0) atomicOr(&bits[r >> 5], 1u << (r & 31));
+    }
+}
+
+// Tracker.__associatedMeasurements__[i] (tracker.py:83,331-332,1226-1227): the (scanNumber, measurementNumber) pairs
+// of every node below the tree's root, i.e. Target.getMeasurementSet of the root (pyTarget.py:414-430), after the
+// last scan's pruning.  MHT_E_CAPACITY: *n holds the required count.
+extern "C" int mht_forest_measurement_set(mht_forest *f, int32_t slot, int32_t cap, int32_t *n, int32_t *h_scan,
+                                          int32_t *h_meas) {
+    if (!f || !n || slot < 0 || slot >= f->T || f->open_scan) {
+        set_error("mht_forest_measurement_set: invalid argument (or a grown scan is still open)");
+        return MHT_E_INVALID;
+    }
+    *n = 0;
+    if (!f->h_alive[slot] || f->scan == 0) return MHT_OK;
+    cudaStream_t s = f->stream;
+    int range[2];
+    MHT_CUDA(cudaMemcpyAsync(&range[0], f->ts.live_lo + slot, 4, cudaMemcpyDeviceToHost, s));
+    MHT_CUDA(cudaMemcpyAsync(&range[1], f->ts.live_hi + slot, 4, cudaMemcpyDeviceToHost, s));
+    MHT_CUDA(cudaStreamSynchronize(s));
+    // the (tree, row) bitmap of the gate stage is rebuilt at the start of every scan: its first row is free here
+    MHT_CUDA(cudaMemsetAsync(f->tm_bits, 0, sizeof(unsigned) * (size_t)f->tm_words, s));
+    if (range[1] > range[0]) {
+        count_launch(), measurement_set_kernel<<<kSMs, 256, 0, s>>>(f->rows[f->scan & 1], f->cap_nodes, f->W, range[0], range[1],
+                                                    f->tm_bits);
+        MHT_CUDA(cudaGetLastError());
+    }
+    std::vector<unsigned> bits(f->tm_words);
+    MHT_CUDA(cudaMemcpyAsync(bits.data(), f->tm_bits, sizeof(unsigned) * (size_t)f->tm_words, cudaMemcpyDeviceToHost, s));
+    MHT_CUDA(cudaStreamSynchronize(s));
+    int k = 0;
+    for (int wd = 0; wd < f->tm_words; ++wd) {
+        unsigned m = bits[wd];
+        while (m) {
+            const int b = __builtin_ctz(m);
+            m &= m - 1;
+            const int r = wd * 32 + b, plane = r / f->cfg.max_meas, idx = r % f->cfg.max_meas;
+            int sc = f->scan - ((f->scan - plane) % f->W + f->W) % f->W;      // latest scan <= now stored in this plane
+            if (sc <= f->h_root_scan[slot]) continue;                          // at or above the (new) root
+            if (k < cap && h_scan && h_meas) {
+                h_scan[k] = sc;
+                h_meas[k] = idx + 1;
+            }
+            ++k;
+        }
+    }
+    *n = k;
+    if (k > cap) {
+        set_error("mht_forest_measurement_set: %d pairs exceed cap %d", k, cap);
+        return MHT_E_CAPACITY;
+    }
+    return MHT_OK;
+}
+
 // mht_forest_history for EVERY live track in one go: the window walks of all tracks share kDeadChunk-wide launches
 // (4 launches for 1000 tracks instead of 1000 single-thread launches with a stream sync each).
 extern "C" int mht_forest_histories(mht_forest *f, int32_t cap_tracks, int32_t cap_len, int32_t *n_tracks,

@@ -389,6 +389,26 @@ class Tracker:
             self.__trackNodes__ = nodes
         return self.__trackNodes__
 
+    @property
+    def __associatedMeasurements__(self):
+        """Per live track: the set of (scanNumber, measurementNumber) used anywhere in its hypothesis tree below the root
+        (reference tracker.py:83,331-332,1226-1227), read from the device on access."""
+        out = []
+        for slot in self._slots:
+            cap = 4096
+            while True:
+                n = C.c_int32()
+                sc = np.zeros(cap, dtype=np.int32)
+                me = np.zeros(cap, dtype=np.int32)
+                rc = self._lib.mht_forest_measurement_set(self._forest, slot, cap, C.byref(n), _lib.ptr(sc), _lib.ptr(me))
+                if rc == _lib.MHT_E_CAPACITY:
+                    cap = n.value + 16
+                    continue
+                _lib.check(rc)
+                break
+            out.append(set(zip(sc[:n.value].tolist(), me[:n.value].tolist())))
+        return out
+
     def getLeafNodes(self, trackIndex):
         """Leaves of one track tree in the reference's DFS order (Target.getLeafNodes)."""
         slot = self._slots[trackIndex]

@@ -551,3 +551,20 @@ def test_histories_of_all_tracks_in_one_call():
         assert len(nodes) > 50 and launches <= 2, (k, len(nodes), launches)
         checked += 1
     assert checked == 6
+
+
+@pytest.mark.parametrize("name", ["cfg5_n8", "cfg2_small"])
+def test_associated_measurements_match_oracle(name):
+    """Tracker.__associatedMeasurements__ (tracker.py:83; recomputed from the new root after every N-scan prune,
+    tracker.py:1226-1227 / pyTarget.py:414-430) against the oracle's sets, scan by scan, through window fill and pruning."""
+    g = golden(name)
+    T, lam_phi, lam_nu, N, Pd, eta2, R = [float(v) for v in g["params"]]
+    orc = mo.OracleTracker(T, lam_phi, lam_nu, eta2=eta2, N=int(N), P_d=Pd)
+    for x in g["init_x"]:
+        orc.initiate(x, float(g["init_time"]))
+    for k, g, pre, trk, nodes, hist, info in _replay_tracker(name):
+        orc.add_scan(g[pre + "z"], float(g[pre + "time"]))
+        got = trk.__associatedMeasurements__
+        assert len(got) == len(orc.assoc), k
+        for i, (a, b) in enumerate(zip(got, orc.assoc)):
+            assert a == {(int(s), int(m)) for s, m in b}, (name, k, i, sorted(a ^ set(b))[:6])
