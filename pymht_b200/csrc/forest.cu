@@ -152,6 +152,7 @@ struct ScanArgs {
     int2 *heavy_list;            // worklist (live index, tree) of leaves gated by the warp-per-leaf kernel
     int *heavy_n;
     int heavy_rows, heavy_cand;  // thresholds: grid rows / candidate measurements under the gate box
+    int use_tma;                 // emit kernel: stage the warps' gated-list tiles with cp.async.bulk + mbarrier
     unsigned *tm_bits;           // [max_trees][tm_words] (tree, measurement) pairs already linked this scan
     int tm_words;
     long long *pool_ctr;
@@ -583,7 +584,35 @@ __global__ void __launch_bounds__(1024, 1) forest_scan_tiles_kernel(ScanArgs a) 
 //            list (inline, or its run in the pool), filter, score, and every field stored coalesced.
 constexpr int kEmitD = 8;    // doubles per leaf in smem: xbar[4] zhat[2] base_cnllr miss_cnllr
 __host__ __device__ inline size_t emit_warp_bytes(int W) {
-    return (size_t)32 * kEmitD * 8 + (size_t)(3 + W) * 32 * 4 + 36 * 4 + 32 * kInline * 4;
+    return (size_t)32 * kEmitD * 8 + (size_t)(3 + W) * 32 * 4 + 36 * 4 + 32 * kInline * 4 + 16;   // + the warp's mbarrier
+}
+
+// ---- TMA (bulk async copy engine) staging of a warp's tile: one cp.async.bulk global -> shared, completion on an mbarrier ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" ::"r"(count), "r"(smem_u32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load_tile(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+    // generic-proxy reads of the previous tile are ordered before the async-proxy write (the warp synchronised already)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "MHT_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "@P1 bra MHT_DONE;\n\t"
+        "bra MHT_WAIT;\n\t"
+        "MHT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(phase), "r"(0x989680u)
+        : "memory");
 }
 __host__ __device__ inline size_t emit_smem_bytes(int W) { return (kTile / 32) * emit_warp_bytes(W); }
 
@@ -598,8 +627,14 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, const in
     int *s_ent = s_tree + 32;                  // [32] pattern-table entry
     int *s_pat = s_ent + 32;                   // [32] hit/miss history of the leaf
     int *s_off = s_pat + 32;                   // [33] child offsets inside the warp (+3 pad)
-    int *s_lst = s_off + 36;                   // [32][kInline] the leaves' sorted gated lists
+    int *s_lst = s_off + 36;                   // [32][kInline] the leaves' sorted gated lists (16-byte aligned: TMA destination)
     int *s_path = s_lst + 32 * kInline;        // [W][32]
+    unsigned long long *s_bar = (unsigned long long *)(s_path + a.W * 32);   // the warp's mbarrier
+    unsigned bar_phase = 0;
+    if (a.use_tma) {
+        if (lane == 0) mbar_init(s_bar, 1);
+        __syncwarp();
+    }
     const int np = *a.d_np;
     const int nwt = (np + 31) >> 5;
     const int W = a.W;
@@ -609,6 +644,9 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, const in
         const int i = wt * 32 + lane;
         const int tile = (wt * 32) / kTile;
         const bool valid = i < np;
+        // the 32 leaves' inline lists are ONE contiguous, 16-byte aligned 2 KB block: the TMA engine stages it while the
+        // lanes fetch the rest of phase A (waited for right before phase B)
+        if (a.use_tma && lane == 0) bulk_load_tile(s_lst, a.glist + (size_t)kInline * (size_t)wt * 32, 32 * kInline * 4, s_bar);
         const int tile_base = a.tile_sum[tile], tile_end = a.tile_sum[tile + 1];
         const int off_i = valid ? tile_base + a.count[i] : tile_end;
         const int off_n = (valid && i + 1 < np && ((i + 1) & (kTile - 1))) ? tile_base + a.count[i + 1] : tile_end;
@@ -632,7 +670,7 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, const in
             const bool take = w < W && back != 0 && a.scan - back > root_scan;
             rr[w] = take ? a.rows_prev[(long long)w * a.stride + pos] : -1;
         }
-        {   // the leaf's inline list -> shared memory (only the quarters that hold entries)
+        if (!a.use_tma) {   // the leaf's inline list -> shared memory (only the quarters that hold entries)
             const int nl = off_n - off_i - 1;
             if (valid && nl <= kInline) {
                 const int4 *src = (const int4 *)(a.glist + (size_t)kInline * i);
@@ -670,6 +708,10 @@ __global__ void __launch_bounds__(kTile) forest_emit_kernel(ScanArgs a, const in
             }
         }
         __syncwarp();
+        if (a.use_tma) {
+            mbar_wait(s_bar, bar_phase);
+            bar_phase ^= 1u;
+        }
         for (int c0 = 0; c0 < total; c0 += 32) {
             const int c = c0 + lane;
             const bool live = c < total;
@@ -1142,6 +1184,8 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
     static const int heavy_cand = getenv("MHT_HEAVY_CAND") ? atoi(getenv("MHT_HEAVY_CAND")) : 40;
     a.heavy_rows = heavy_rows;
     a.heavy_cand = heavy_cand;
+    static const int emit_tma = getenv("MHT_EMIT_TMA") ? atoi(getenv("MHT_EMIT_TMA")) : 1;
+    a.use_tma = emit_tma;
     a.heavy_n = f->d_np + 2;
     a.pool_ctr = (long long *)(f->d_np + 4);
     a.pt_gate = f->pt_gate;
