@@ -116,7 +116,7 @@ def make_tracker(name, n_scans=1 << 30):
     from pymht_b200.models import pv
     nT, R, lam, N, Pd, seed, max_nodes, max_par = WORKLOADS[name]
     max_nodes, max_par = capacities(name, n_scans)
-    trk = Tracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=meas_capacity(name),
+    trk = Tracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, initiator=None, maxTargets=max(1024, nT + 24), maxMeasurements=meas_capacity(name),
                   maxNodes=max_nodes, maxParents=max_par,
                   maxDualIterations=int(os.environ.get("MHT_DUAL_ITERS", "120")))
     trk.mergeThreshold = 0.0
@@ -473,7 +473,7 @@ def run_tree_sharded(args, name, config, dist, torch, rank, world, local_rank, p
     #      an uncertified one depends on which worker found which incumbent first, so only scans certified on BOTH
     #      sides are compared (and the tracks a later scan inherits are only comparable while that holds) ----
     n_verify = 2
-    vt = ShardedTracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=mcap,
+    vt = ShardedTracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, initiator=None, maxTargets=max(1024, nT + 24), maxMeasurements=mcap,
                         maxNodes=1 << 22, maxParents=1 << 20, exactBudgetMs=10000)
     vt.mergeThreshold = 0.0
     vt.preInitialize(simList)
@@ -485,7 +485,7 @@ def run_tree_sharded(args, name, config, dist, torch, rank, world, local_rank, p
     vt.close()
     v_single, v_cert1 = None, None
     if rank == 0:
-        st = Tracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=mcap,
+        st = Tracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, initiator=None, maxTargets=max(1024, nT + 24), maxMeasurements=mcap,
                      maxNodes=1 << 22, maxParents=1 << 20, exactBudgetMs=10000)
         st.mergeThreshold = 0.0
         st.preInitialize(simList)
@@ -497,7 +497,7 @@ def run_tree_sharded(args, name, config, dist, torch, rank, world, local_rank, p
         st.close()
 
     per = 1.0 / world + 0.15
-    trk = ShardedTracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, maxTargets=max(1024, nT + 24), maxMeasurements=mcap,
+    trk = ShardedTracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd, initiator=None, maxTargets=max(1024, nT + 24), maxMeasurements=mcap,
                          maxNodes=int(max_nodes * per), maxParents=int(max_par * per),
                          maxDualIterations=int(os.environ.get("MHT_DUAL_ITERS", "120")))
     trk.mergeThreshold = 0.0

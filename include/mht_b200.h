@@ -277,6 +277,49 @@ int mht_forest_min_leaf_distance(mht_forest *f, double px, double py, double *di
 int mht_forest_leaves(mht_forest *f, int32_t slot, int64_t cap, int64_t *n, double *h_x, double *h_cnllr,
                       int32_t *h_meas);
 
+/* ---- M-of-N track initiator (reference pymht/initiators/m_of_n.py:233-478) ----------------------------------------
+ * The step after the hot path: it consumes the unused-measurement mask the gate stage returns
+ * (tracker.py:266-277).  The host class pymht_b200.initiators.m_of_n.Initiator keeps the O(n) bookkeeping of the
+ * preliminary tracks; the O(n1 x n2) parts run here:
+ *   mht_gnn_assign  replaces _solve_global_nearest_neighbour (m_of_n.py:24-104) TOGETHER with the dense distance /
+ *                   NIS matrix its two callers build first (_processInitiators :385-396, _processPreliminaryTracks
+ *                   :284-303).  The reference pads the gated matrix to a square one and runs an O(n^3) Munkres on it; its
+ *                   optimum is the maximum-cardinality, then minimum-distance matching of the gated pairs, which is what
+ *                   this solves exactly on the sparse gated graph (csrc/gnn_core.h), one thread block per component.
+ *   mht_gnn_similar replaces the all-pairs PreliminaryTrack.compareSimilarity loop of __spawn_preliminary_tracks
+ *                   (m_of_n.py:196-201, 462-470). */
+typedef struct mht_gnn mht_gnn; /* opaque: device buffers sized at creation */
+
+typedef struct mht_gnn_info {
+    int32_t n_edges;            /* gated pairs */
+    int32_t n_components;       /* connected components with at least one pair */
+    int32_t largest_component;  /* rows of the largest one */
+    int32_t n_assigned;
+    int32_t searches, rounds;   /* block-wide augmenting-path searches and the frontier rounds they took */
+    int32_t batches;            /* batches of concurrent (one warp each) searches before them */
+    int32_t spec_commits;       /* searches committed by those batches */
+    int32_t spec_overflow;      /* rows whose search outgrew the per-warp table (left to the block-wide search) */
+    int32_t reserved;
+    float ms_gate, ms_solve;    /* device time: gating + CSR build, components + assignment */
+} mht_gnn_info;
+
+int mht_gnn_create(int64_t max_rows, int64_t max_cols, int64_t max_edges, mht_gnn **out);
+void mht_gnn_destroy(mht_gnn *h);
+
+/* mode 0 (m_of_n.py:385-401): rows = initiators (previous scan's leftover measurements), columns = unused measurements;
+ *   a pair is gated when its Euclidean distance (float64 norm of the float32 difference) is <= gate (= v_max * dt).
+ * mode 1 (m_of_n.py:284-303): rows = predicted measurements of the preliminary tracks with h_row_sinv[n_rows][4] = S^-1
+ *   (float32, row-major); a pair is gated when its float32 NIS is <= gate (chi2 0.99 quantile); cost = float32 distance.
+ * h_match[i] = assigned column of row i or -1.  HOST pointers; MHT_E_CAPACITY when the gated pairs exceed max_edges. */
+int mht_gnn_assign(mht_gnn *h, int mode, int64_t n_rows, const float *h_row_xy, const float *h_row_sinv, int64_t n_cols,
+                   const float *h_col_xy, double gate, int32_t *h_match, mht_gnn_info *info);
+
+/* h_state[n_tracks + n_cand][4], h_sinv[n_tracks + n_cand][16] (inverse of covariance + R_ais of that entry, float32):
+ * candidate k is compared with every entry in front of it (all existing tracks and the candidates 0..k-1);
+ * pairs (k, entry) with NIS = d^T S_entry^-1 d <= threshold are returned in h_pairs[2 * n_pairs] (unordered). */
+int mht_gnn_similar(mht_gnn *h, int64_t n_tracks, int64_t n_cand, const float *h_state, const float *h_sinv,
+                    double threshold, int32_t *h_pairs, int64_t cap_pairs, int64_t *n_pairs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -160,6 +160,87 @@ def run_reference(name):
     return out
 
 
+def _init_scenario(name):
+    """(n_targets, n_scans, radarRange, lambda_phi, N, P_d, seed) of the fixtures with the M-of-N initiator LIVE."""
+    if name == "init_small":
+        # 15 targets, ~80 clutter points per scan: small connected components in both assignment problems
+        return 15, 14, 500.0, 1e-4, 4, 0.9, 911
+    if name == "init_dense":
+        # BASELINE config 3's clutter density (1e-3 / m^2) on a small disc: ~280 clutter points per scan, 7.9 of them
+        # inside every initiator's 50 m gate -> the initiator's assignment problem is ONE giant component
+        return 8, 10, 300.0, 1e-3, 3, 0.9, 912
+    raise KeyError(name)
+
+
+def run_reference_initiator(name):
+    """The unmodified reference with its own M-of-N initiator (pymht/initiators/m_of_n.py) and NO pre-initialised tracks:
+    every track is born by the initiator.  Stored per scan: what Initiator.processMeasurements was given (the unused
+    measurements), what it returned (initial targets) and its state afterwards (preliminary tracks, initiators), plus the
+    tracker's tracks like the other fixtures."""
+    ref_shim.install()
+    import pymht.utils.simulator as sim
+    import pymht.models.pv as pv
+    import pymht.tracker as rtracker
+    import pymht.utils.helpFunctions as hpf
+
+    nT, n_scans, R, lam, N, Pd, seed = _init_scenario(name)
+    sim.seed_simulator(seed)
+    p0 = np.array([0.0, 0.0])
+    init = sim.generateInitialTargets(nT, p0, R * 0.8, Pd, pv.sigmaQ_true)
+    for tgt in init:
+        tgt.time = T0
+    simList = sim.simulateTargets(init, n_scans * T_RADAR, T_RADAR, pv)
+    scans = sim.simulateScans(simList, T_RADAR, pv.C_RADAR, pv.R_RADAR(pv.sigmaR_RADAR_true), lam, R, p0,
+                              shuffle=True, localClutter=False, globalClutter=True, preInitialized=False)
+    trk = rtracker.Tracker(pv, T_RADAR, lam, 1e-9, N=N, P_d=Pd)
+    ini = trk.initiator
+    rec = {}
+    orig = ini.processMeasurements
+
+    def spy(radar, ais=list()):
+        rec["in_z"] = np.array(radar.measurements, dtype=np.float32).reshape(-1, 2)
+        rec["in_time"] = radar.time
+        out = orig(radar, ais)
+        rec["out"] = out
+        return out
+    ini.processMeasurements = spy
+    out = {"n_scans": np.int64(len(scans)), "params": np.array([T_RADAR, lam, 1e-9, N, Pd, 5.99, R]),
+           "init_params": np.array([ini.M, ini.N, ini.v_max, ini.merge_threshold, ini.gamma])}
+    for k, scan in enumerate(scans):
+        t = time.time()
+        trk.addMeasurementList(scan)
+        wall = time.time() - t
+        nodes = list(trk.getTrackNodes())
+        hist = hpf.backtrackMeasurementNumbers(nodes)
+        width = max([len(h) for h in hist], default=0)
+        H = -np.ones((len(nodes), width), dtype=np.int64)
+        for i, h in enumerate(hist):
+            H[i, :len(h)] = h
+        pre = "s%d_" % k
+        out[pre + "z"] = np.asarray(scan.measurements, dtype=np.float32)
+        out[pre + "time"] = np.float64(scan.time)
+        out[pre + "ids"] = np.array([n.ID for n in nodes], dtype=np.int64)
+        out[pre + "hist"] = H
+        out[pre + "x"] = np.array([n.x_0 for n in nodes], dtype=np.float64).reshape(len(nodes), 4)
+        out[pre + "cnllr"] = np.array([n.cumulativeNLLR for n in nodes], dtype=np.float64)
+        out[pre + "ini_z"] = rec["in_z"]
+        out[pre + "ini_time"] = np.float64(rec["in_time"])
+        new = rec["out"]
+        out[pre + "new_x"] = np.array([t_.x_0 for t_ in new], dtype=np.float64).reshape(len(new), 4)
+        out[pre + "new_P"] = np.array([t_.P_0 for t_ in new], dtype=np.float64).reshape(len(new), 4, 4)
+        out[pre + "new_meas"] = np.array([t_.measurement for t_ in new], dtype=np.float64).reshape(len(new), 2)
+        pt = ini.preliminary_tracks
+        out[pre + "pt_state"] = np.array([p_.state for p_ in pt], dtype=np.float64).reshape(len(pt), 4)
+        out[pre + "pt_cov"] = np.array([p_.covariance for p_ in pt], dtype=np.float64).reshape(len(pt), 4, 4)
+        out[pre + "pt_mn"] = np.array([[p_.m, p_.n] for p_ in pt], dtype=np.int64).reshape(len(pt), 2)
+        out[pre + "initiators"] = np.array([i_.value for i_ in ini.initiators], dtype=np.float32).reshape(-1, 2)
+        out[pre + "toc_init"] = np.float64(trk.toc["Init"])
+        print("%s scan %d: M=%d unused=%d new=%d prelim=%d initiators=%d tracks=%d init=%.2fs wall=%.2fs" % (
+            name, k + 1, len(scan.measurements), len(rec["in_z"]), len(new), len(pt), len(ini.initiators),
+            len(nodes), trk.toc["Init"], wall), flush=True)
+    return out
+
+
 def kalman_kat():
     """Outputs of the reference's own kalman.py functions on seeded random leaves."""
     ref_shim.install()
@@ -192,7 +273,12 @@ def main(argv):
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     names = argv or ["kalman_kat", "cfg1_crossing", "cfg2_small", "cfg5_small", "cfg2", "cfg3_head"]
     for name in names:
-        data = kalman_kat() if name == "kalman_kat" else run_reference(name)
+        if name == "kalman_kat":
+            data = kalman_kat()
+        elif name.startswith("init_"):
+            data = run_reference_initiator(name)
+        else:
+            data = run_reference(name)
         np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **data)
         print("wrote", name)
 

@@ -56,6 +56,16 @@ class ScanInfo(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class GnnInfo(C.Structure):
+    _fields_ = [("n_edges", C.c_int32), ("n_components", C.c_int32), ("largest_component", C.c_int32),
+                ("n_assigned", C.c_int32), ("searches", C.c_int32), ("rounds", C.c_int32),
+                ("batches", C.c_int32), ("spec_commits", C.c_int32), ("spec_overflow", C.c_int32),
+                ("reserved", C.c_int32), ("ms_gate", C.c_float), ("ms_solve", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 _vp, _i64, _i32, _dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
 _SIGNATURES = {
     "mht_version": (C.c_int, []),
@@ -90,6 +100,10 @@ _SIGNATURES = {
     "mht_forest_measurement_set": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i32), _vp, _vp]),
     "mht_forest_min_leaf_distance": (C.c_int, [_vp, _dbl, _dbl, C.POINTER(_dbl)]),
     "mht_forest_leaves": (C.c_int, [_vp, _i32, _i64, C.POINTER(_i64), _vp, _vp, _vp]),
+    "mht_gnn_create": (C.c_int, [_i64, _i64, _i64, C.POINTER(_vp)]),
+    "mht_gnn_destroy": (None, [_vp]),
+    "mht_gnn_assign": (C.c_int, [_vp, C.c_int, _i64, _vp, _vp, _i64, _vp, _dbl, _vp, C.POINTER(GnnInfo)]),
+    "mht_gnn_similar": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _dbl, _vp, _i64, C.POINTER(_i64)]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

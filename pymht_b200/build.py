@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmht_b200.so")
-SOURCES = ["api.cu", "gate.cu", "assoc.cu", "forest.cu"]
+SOURCES = ["api.cu", "gate.cu", "assoc.cu", "forest.cu", "initiator.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
               "-std=c++17", "-Xcompiler", "-fPIC",
               "-cudart", "static"]

@@ -1142,7 +1142,10 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
         }
         f->h_level_nodes = 0;
         f->last_tracks.clear();
-        if (info) memset(info, 0, sizeof(*info));
+        if (info) {
+            memset(info, 0, sizeof(*info));
+            info->certified = 1;   // nothing to associate
+        }
         if (h_used && M) memset(h_used, 0, (size_t)M);
         return MHT_OK;
     }

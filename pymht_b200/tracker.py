@@ -8,9 +8,11 @@ _findClustersFromSets (:961-974), _solveOptimumAssociation/_solveBLP_OR_TOOLS (:
 __analyzeTrackTermination/_terminateTracks (:891-916,:353-381), _nScanPruning (:1219-1231).
 Kept call-compatible: __init__ kwargs, preInitialize, initiateTarget, addMeasurementList,
 getTrackNodes, runtimeLog/toc keys, getRuntimeAverage.
-Out of scope (fail loudly): AIS fusion, plotting, XML export, dynamicWindow, pruneSimilar.
-The M-of-N initiator is out of scope: `self.initiator` defaults to a null object; any object with
-processMeasurements(unusedRadar, unusedAis) -> [Target] can be plugged in (tracker.py:266-277).
+Out of scope (fail loudly): AIS fusion, plotting, XML export, pruneSimilar.
+Step 7 (tracker.py:266-277): `self.initiator` is the M-of-N initiator like in the reference (tracker.py:62-72), with its
+assignment problems on the GPU (pymht_b200/initiators/m_of_n.py); `Tracker(..., initiator=None)` nulls it (what the
+benchmark configurations of SURVEY.md 8d do), and any object with processMeasurements(unusedRadar, unusedAis) -> [Target]
+can be plugged in.
 """
 import ctypes as C
 import logging
@@ -46,7 +48,19 @@ class Tracker:
         self.R_RADAR = model.R_RADAR()
         self.Q = model.Q(radarPeriod)
         self.mergeThreshold = 4 * (model.sigmaR_RADAR_tracker ** 2)
-        self.initiator = NullInitiator()
+        # target initiator (tracker.py:62-72)
+        self.maxSpeedMS = kwargs.get("maxSpeedMS", 20)
+        self.M_required = kwargs.get("M_required", 2)
+        self.N_checks = kwargs.get("N_checks", 3)
+        which = kwargs.get("initiator", "m_of_n")
+        if which is None or which is False:
+            self.initiator = NullInitiator()
+        elif which == "m_of_n" or which is True:
+            from .initiators import m_of_n
+            self.initiator = m_of_n.Initiator(self.M_required, self.N_checks, self.maxSpeedMS, self.C, self.R_RADAR,
+                                              self.mergeThreshold)
+        else:
+            self.initiator = which
 
         self.__targetList__ = []            # root views, one per live track
         self.__targetWindowSize__ = []
@@ -148,7 +162,8 @@ class Tracker:
         _lib.check(self._lib.mht_forest_initiate(self._forest, _lib.ptr(x0), _lib.ptr(P0), float(self.default_P_d),
                                                  C.byref(slot)))
         node = Target(newTarget.time, len(self.__scanHistory__), x0.copy(), P0.copy(), ID=self.trackIdCounter,
-                      P_d=self.default_P_d, status=newTarget.status, isRoot=True)
+                      P_d=self.default_P_d, status=newTarget.status, isRoot=True,
+                      measurementNumber=newTarget.measurementNumber, measurement=newTarget.measurement)
         self.trackIdCounter += 1
         current = self.getTrackNodes()
         self._slots.append(slot.value)

@@ -39,7 +39,7 @@ def test_no_cpu_fallback_without_device():
     lib = _lib.load()
     assert lib.mht_device_count() == 0
     with pytest.raises(_lib.MhtError) as e:
-        Tracker(pv, 2.5, 1e-4, 1e-9)
+        Tracker(pv, 2.5, 1e-4, 1e-9, initiator=None)
     assert e.value.code == _lib.MHT_E_NODEVICE
 
 

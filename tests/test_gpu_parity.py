@@ -161,7 +161,7 @@ def _replay_tracker(name, n_scans=None, scan_kw=None, setup=None, **kw):
     from pymht_b200.utils.classDefinitions import MeasurementList
     g = golden(name)
     T, lam_phi, lam_nu, N, Pd, eta2, R = [float(v) for v in g["params"]]
-    trk = Tracker(pv, T, lam_phi, lam_nu, eta2=eta2, N=int(N), P_d=Pd, **kw)
+    trk = Tracker(pv, T, lam_phi, lam_nu, eta2=eta2, N=int(N), P_d=Pd, initiator=kw.pop("initiator", None), **kw)
     trk.mergeThreshold = 0.0
     if setup:
         setup(trk)
@@ -314,7 +314,7 @@ def test_large_random_forest_properties():
     init = sim.generateInitialTargets(nT, np.zeros(2), R, 0.9, 1.0)
     simList = sim.simulateTargets(init, 5 * 2.5, 2.5, pv)
     scans = sim.simulateScans(simList, 2.5, pv.C_RADAR, pv.R_RADAR(), lam, R, np.zeros(2), preInitialized=True)
-    trk = Tracker(pv, 2.5, lam, 1e-9, N=6, P_d=0.9, maxTargets=1024, maxNodes=1 << 23, maxParents=1 << 21)
+    trk = Tracker(pv, 2.5, lam, 1e-9, N=6, P_d=0.9, initiator=None, maxTargets=1024, maxNodes=1 << 23, maxParents=1 << 21)
     trk.mergeThreshold = 0.0
     trk.preInitialize(simList)
     for scan in scans[:5]:
@@ -334,7 +334,7 @@ def _small_tracker(**kw):
     from pymht_b200.models import pv
     args = dict(N=3, P_d=0.9, maxTargets=8, maxNodes=1 << 12, maxParents=1 << 10, maxMeasurements=256)
     args.update(kw)
-    trk = Tracker(pv, 2.5, 1e-4, 1e-9, **args)
+    trk = Tracker(pv, 2.5, 1e-4, 1e-9, initiator=None, **args)
     trk.mergeThreshold = 0.0
     return trk, pv
 
@@ -435,7 +435,7 @@ def test_dense_gate_heavy_paths_vs_oracle():
     from pymht_b200.utils.classDefinitions import MeasurementList
     rng = np.random.RandomState(5)
     x0 = np.array([50.0, -20.0, 2.0, 1.0])
-    trk = Tracker(pv, 2.5, 1e-3, 1e-9, N=3, P_d=0.9, maxTargets=8, maxNodes=1 << 20, maxParents=1 << 16,
+    trk = Tracker(pv, 2.5, 1e-3, 1e-9, N=3, P_d=0.9, initiator=None, maxTargets=8, maxNodes=1 << 20, maxParents=1 << 16,
                   maxMeasurements=4096)
     trk.mergeThreshold = 0.0
     orc = mo.OracleTracker(2.5, 1e-3, 1e-9, eta2=5.99, N=3, P_d=0.9)

@@ -26,7 +26,7 @@ def _worker(rank, world, port, name, n_scans, out):
     from pymht_b200.utils.classDefinitions import MeasurementList
     g = golden(name)
     T, lam_phi, lam_nu, N, Pd, eta2, R = [float(v) for v in g["params"]]
-    trk = ShardedTracker(pv, T, lam_phi, lam_nu, eta2=eta2, N=int(N), P_d=Pd, maxTargets=256, maxNodes=1 << 18,
+    trk = ShardedTracker(pv, T, lam_phi, lam_nu, eta2=eta2, N=int(N), P_d=Pd, initiator=None, maxTargets=256, maxNodes=1 << 18,
                          maxParents=1 << 16, maxMeasurements=4096)
     trk.mergeThreshold = 0.0
     lo, hi = shard_bounds(len(g["init_x"]), world, rank)

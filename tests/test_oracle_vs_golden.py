@@ -103,3 +103,28 @@ def test_replay_cfg5_full():
 def test_replay_cfg2_long():
     """BASELINE config 2 for 30 scans: 25 scans of steady state (N-scan pruning, terminations, re-clustering)."""
     replay("cfg2_long", n_scans=30)
+
+
+@pytest.mark.parametrize("name", ["init_small", "init_dense"])
+def test_initiator_oracle_vs_reference_fixture(name):
+    """oracle/initiator_oracle.py (restatement of pymht/initiators/m_of_n.py:233-478) against what the unmodified reference's
+    initiator returned and held after every scan (oracle/gen_golden.py run_reference_initiator)."""
+    from oracle.initiator_oracle import InitiatorOracle
+    g = golden(name)
+    M, N, vmax, thr, gamma = g["init_params"]
+    C = np.zeros((2, 4), np.float32)
+    C[0, 0] = C[1, 1] = 1
+    o = InitiatorOracle(int(M), int(N), vmax, C, (np.eye(2) * 6.25).astype(np.float32), thr)
+    assert abs(o.gamma - gamma) < 1e-12
+    for k in range(int(g["n_scans"])):
+        pre = "s%d_" % k
+        new = o.processMeasurements(g[pre + "ini_z"], float(g[pre + "ini_time"]))
+        nx = np.array([n[0] for n in new]).reshape(-1, 4)
+        assert nx.shape == g[pre + "new_x"].shape, (name, k)
+        assert np.allclose(nx, g[pre + "new_x"], rtol=1e-6, atol=1e-6)
+        assert np.allclose(np.array([n[1] for n in new]).reshape(-1, 4, 4), g[pre + "new_P"], rtol=1e-6, atol=1e-6)
+        st = np.array([p.state for p in o.preliminary_tracks]).reshape(-1, 4)
+        assert st.shape == g[pre + "pt_state"].shape, (name, k)
+        assert np.allclose(st, g[pre + "pt_state"], rtol=1e-6, atol=1e-6)
+        assert np.array_equal(np.array([[p.m, p.n] for p in o.preliminary_tracks]).reshape(-1, 2), g[pre + "pt_mn"])
+        assert np.array_equal(o.initiators, g[pre + "initiators"])
