@@ -244,8 +244,8 @@ struct Claims {                       // [n_rows] / [n_cols] keys: (inverted epo
 
 // priority of a search inside its batch (smaller wins): the searches that scanned MORE rows first -- they are the ones that are
 // expensive to repeat -- then the smaller row index.  Depends on the data only.
-GNN_HD unsigned long long claim_prio(int rows_scanned, int row) {
-    const int cls = 1023 - (rows_scanned < 1023 ? rows_scanned : 1023);
+GNN_HD unsigned long long claim_prio(int rows_scanned, int row, bool size_first = true) {
+    const int cls = size_first ? 1023 - (rows_scanned < 1023 ? rows_scanned : 1023) : 0;
     return ((unsigned long long)cls << 30) | (unsigned)row;
 }
 GNN_HD unsigned long long claim_key(unsigned epoch, unsigned long long prio) {
@@ -364,8 +364,8 @@ GNN_HD void spec_search(W &w, const Graph &g, const State &st, Spec *sp, int s, 
 }
 
 template <class W>
-GNN_HD void spec_claim(W &w, const Spec *sp, Claims cl, unsigned epoch) {
-    const unsigned long long key = claim_key(epoch, claim_prio(sp->nR, sp->root));
+GNN_HD void spec_claim(W &w, const Spec *sp, Claims cl, unsigned epoch, bool size_first = true) {
+    const unsigned long long key = claim_key(epoch, claim_prio(sp->nR, sp->root, size_first));
     const double delta = sp->best;
     for (int k = w.lane(); k < sp->nR; k += w.nlanes()) {
         w.amin64(&cl.touch_r[sp->r_id[k]], key);
@@ -379,8 +379,8 @@ GNN_HD void spec_claim(W &w, const Spec *sp, Claims cl, unsigned epoch) {
 
 // true iff no search of this batch with a higher priority (smaller claim_prio) interferes
 template <class W>
-GNN_HD bool spec_check(W &w, const Spec *sp, Claims cl, unsigned epoch) {
-    const unsigned long long s = claim_prio(sp->nR, sp->root);
+GNN_HD bool spec_check(W &w, const Spec *sp, Claims cl, unsigned epoch, bool size_first = true) {
+    const unsigned long long s = claim_prio(sp->nR, sp->root, size_first);
     const double delta = sp->best;
     int ok = 1;
     for (int k = w.lane(); k < sp->nR; k += w.nlanes()) {

@@ -53,6 +53,8 @@ struct mht_gnn {
     mht::GnnBuf b;
     int *hdr_h;          // pinned
     int spec_grid;       // blocks of the speculative phase (resident at once), 0 = phase off (MHT_GNN_SPEC=0)
+    int spec_row_cap;    // rows one speculative search may scan before it is left to the block-wide search (MHT_GNN_ROWCAP)
+    int spec_size_first; // batch priority: long searches first (1) or smallest row index (0) (MHT_GNN_SIZE_FIRST)
     cudaStream_t stream;
     cudaEvent_t ev[3];
 };
@@ -314,7 +316,7 @@ struct GnnWarpCtx {
 // Speculative parallel phase (gnn_core.h): persistent cooperative kernel, one warp per concurrent search.  Warp w owns the
 // rows w, w + W, w + 2W, ... and works through them in order; a batch = every warp searches its current free row, grid
 // barrier, the non-interfering ones commit, grid barrier.
-__global__ void __launch_bounds__(kGnnSpecWarps * 32) gnn_spec_kernel(int n_rows, int n_cols, GnnBuf b, int max_batches) {
+__global__ void __launch_bounds__(kGnnSpecWarps * 32) gnn_spec_kernel(int n_rows, int n_cols, GnnBuf b, int max_batches, int row_cap, int size_first) {
     extern __shared__ __align__(16) unsigned char spec_smem[];
     cg::grid_group grid = cg::this_grid();
     gnn::Spec *sp = reinterpret_cast<gnn::Spec *>(spec_smem) + (threadIdx.x >> 5);
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(kGnnSpecWarps * 32) gnn_spec_kernel(int n_rows
         }
         if (cursor < n_rows) {
             row = cursor;
-            gnn::spec_search(w, g, b.st, sp, row, BIG);
+            gnn::spec_search(w, g, b.st, sp, row, BIG, row_cap);
             if (w.lane() == 0) atomicAdd(&b.hdr[8 + (epoch & 1)], 1);
             if (sp->overflow) {
                 if (w.lane() == 0) {
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(kGnnSpecWarps * 32) gnn_spec_kernel(int n_rows
                 }
                 row = -1;
             } else {
-                gnn::spec_claim(w, sp, b.cl, epoch);
+                gnn::spec_claim(w, sp, b.cl, epoch, size_first != 0);
             }
         }
         grid.sync();
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(kGnnSpecWarps * 32) gnn_spec_kernel(int n_rows
             b.hdr[8 + ((epoch + 1) & 1)] = 0;
             if (searched) b.hdr[10] += 1;
         }
-        if (row >= 0 && gnn::spec_check(w, sp, b.cl, epoch)) {
+        if (row >= 0 && gnn::spec_check(w, sp, b.cl, epoch, size_first != 0)) {
             gnn::spec_commit(w, g, b.st, sp);
             if (w.lane() == 0) atomicAdd(&b.hdr[11], 1);
         }
@@ -522,6 +524,9 @@ extern "C" int mht_gnn_create(int64_t max_rows, int64_t max_cols, int64_t max_ed
         return MHT_E_CUDA;
     }
     h->spec_grid = 0;
+    const char *cap_env = getenv("MHT_GNN_ROWCAP"), *sf_env = getenv("MHT_GNN_SIZE_FIRST");
+    h->spec_row_cap = cap_env ? std::max(1, std::min(atoi(cap_env), gnn::kSpecRows)) : gnn::kSpecRows;
+    h->spec_size_first = sf_env ? atoi(sf_env) != 0 : 0;
     const char *env = getenv("MHT_GNN_SPEC");
     if (!env || atoi(env) != 0) {
         const size_t smem = kGnnSpecWarps * sizeof(gnn::Spec);
@@ -604,8 +609,8 @@ extern "C" int mht_gnn_assign(mht_gnn *h, int mode, int64_t n_rows, const float 
     gnn_group_kernel<<<1, 1024, 0, s>>>(R, b);
     bool started = false;
     if (h->spec_grid > 0) {
-        int rr = R, cc = Cn, mb = 1 << 20;
-        void *args[] = {&rr, &cc, &b, &mb};
+        int rr = R, cc = Cn, mb = 1 << 20, cap = h->spec_row_cap, sf = h->spec_size_first;
+        void *args[] = {&rr, &cc, &b, &mb, &cap, &sf};
         count_launch();
         MHT_CUDA(cudaLaunchCooperativeKernel((void *)gnn_spec_kernel, dim3(h->spec_grid), dim3(kGnnSpecWarps * 32), args,
                                              kGnnSpecWarps * sizeof(gnn::Spec), s));
