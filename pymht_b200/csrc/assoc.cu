@@ -363,6 +363,54 @@ __device__ __forceinline__ void du_decide_one(const AssocWork &w, int t) {
     }
 }
 
+// du_decide_one with every load issued before the first use (one dependent hop instead of a chain of five); same arithmetic,
+// same stores.
+__device__ __forceinline__ void du_decide_one_hoisted(const AssocWork &w, int t) {
+    const int done = w.cl_done[t];
+    const long long m = w.cl_m[t], us = w.cl_u[t], cs = w.cl_cost[t];
+    const int nrm = w.cl_nrm[t];
+    double best = w.cl_best[t], theta = w.cl_theta[t];
+    const double ub0 = w.cl_ub[t];
+    int stall = w.cl_stall[t];
+    if (done) {
+        w.cl_flag[t] = 0;
+        return;
+    }
+    const double L = from_fix(m - us);
+    if (nrm == 0) {  // conflict-free and complementary: argmins are optimal
+        w.cl_done[t] = 1;
+        w.cl_best[t] = L;
+        w.cl_ub[t] = from_fix(cs);
+        w.cl_flag[t] = 3;
+        w.cl_step[t] = 0.0;
+        atomicOr(&w.stall_ctr[2], 1);
+        return;
+    }
+    int flag = 0;
+    if (L > best + 1e-12) {
+        const bool big = L > best + kBigGain * fmax(1.0, fabs(L));
+        flag = big ? 9 : 1;
+        if (big) atomicOr(&w.stall_ctr[2], 1);
+        best = L;
+        w.cl_best[t] = L;
+        w.cl_stall[t] = 0;
+    } else if (++stall >= kPatience) {
+        theta *= kShrink;
+        w.cl_theta[t] = theta;
+        w.cl_stall[t] = 0;
+    } else {
+        w.cl_stall[t] = stall;
+    }
+    w.cl_flag[t] = flag;
+    if (ub0 - best < 1e-9) {
+        w.cl_done[t] = 1;
+        w.cl_step[t] = 0.0;
+    } else {
+        w.cl_step[t] = ub0 < 1e299 ? theta * (ub0 - L) / (double)nrm : 0.0;
+        atomicAdd(&w.stall_ctr[1], 1);
+    }
+}
+
 __device__ __forceinline__ void du_decide_body(ColView c, AssocWork w) {
     if (du_skip(c, w)) return;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < c.n_trees; t += gridDim.x * blockDim.x) {
@@ -808,9 +856,14 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
         tp = now_;                                                    \
     }
     if (gtid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tp));
+    // every phase below is ONE dependent hop to L2: its loads are issued together, before anything consumes them
+    const bool overflow = c.idx && w.act_n[2];   // loop invariant: set by the active-list kernels before the launch
     for (int it = 0; it < iters; ++it) {
-        if (((volatile int *)w.info)[0]) break;  // uniform: written before the last cluster barrier
+        // stop flag (uniform: written before the last cluster barrier); consumed once phase A's loads are in flight
+        const int stop = ((volatile int *)w.info)[0];
+        bool skip = overflow;     // du_skip(): the subgradient phases are skipped once the solve is finished
         if (it % greedy_every == 0) {
+            if (stop) break;
             dual_rc_body<false>(c, w);
             cluster.sync();
             for (int mode = 0; mode < (it ? 2 : 1); ++mode) {
@@ -829,6 +882,7 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
                 if (blockIdx.x == 0) greedy_finish_body(c, w, w.tstart);
                 cluster.sync();
             }
+            skip = skip || ((volatile int *)w.info)[0] != 0;   // the primal phase may have closed the last gap
             LOOP_PROF(0)
         }
         // ---- phase A, CTA local: reduced costs, per-tree minimum and argmin (ties -> last column) in shared memory,
@@ -838,8 +892,8 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
             s_tmin[tl] = w.tdone[t_first + tl] ? 0ull : kKeyInf;
             s_targ[tl] = -1;
         }
-        __syncthreads();
-        // pass 1: reduced costs -- nothing but loads and adds, so the gathers of a thread's columns overlap
+        // pass 1: reduced costs -- nothing but loads and adds, so the gathers of a thread's columns overlap (with each
+        // other and with the done flags above)
 #pragma unroll 4
         for (int k = threadIdx.x; k < nc; k += blockDim.x) {
             double v = s_cost[k];
@@ -849,6 +903,8 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
             }
             s_rc[k] = v;
         }
+        __syncthreads();
+        if (stop) break;                                  // uniform over the cluster; nothing global was written yet
         // pass 2: per-tree minimum (warp-aggregated over runs of equal tree); key 0 marks a finished tree
         for (int k = threadIdx.x; k < nc_round; k += blockDim.x) {
             int t = -1;
@@ -868,7 +924,7 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
         }
         __syncthreads();
         LOOP_PROF(1)
-        if (!du_skip(c, w)) {
+        if (!skip) {
             const int ntl_round = (ntl + 31) & ~31;
             for (int tl = threadIdx.x; tl < ntl_round; tl += blockDim.x) {
                 const int k = tl < ntl ? s_targ[tl] : -1;
@@ -896,23 +952,33 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
         cluster.sync();
         LOOP_PROF(3)
         // ---- rows: subgradient, norms (this thread's rows) ----
-        if (!du_skip(c, w)) {
+        if (!skip) {
+            int r_done[kClusterRowsPerThread], r_use[kClusterRowsPerThread];
+            double r_u[kClusterRowsPerThread];
+#pragma unroll
+            for (int q = 0; q < kClusterRowsPerThread; ++q) {
+                r_done[q] = 1;
+                r_use[q] = 0;
+                r_u[q] = 0.0;
+                if (q < nq && my_r[q] >= 0) {
+                    r_done[q] = w.cl_done[my_cl[q]];
+                    r_use[q] = w.usage[my_r[q]];
+                    r_u[q] = w.u[my_r[q]];
+                }
+            }
 #pragma unroll
             for (int q = 0; q < kClusterRowsPerThread; ++q) {
                 if (q >= nq) break;                       // uniform
                 const int r = my_r[q], cl = my_cl[q];
                 int g = 0;
                 long long uf = 0;
-                bool active = r >= 0;
+                const bool active = r >= 0 && !r_done[q];
                 if (active) {
-                    active = !w.cl_done[cl];
-                    if (active) {
-                        g = w.usage[r] - 1;
-                        const double ur = w.u[r];
-                        if (ur <= 0.0 && g < 0) g = 0;
-                        w.usage[r] = g;
-                        if (ur > 0.0) uf = to_fix(ur);
-                    }
+                    g = r_use[q] - 1;
+                    const double ur = r_u[q];
+                    if (ur <= 0.0 && g < 0) g = 0;
+                    w.usage[r] = g;
+                    if (ur > 0.0) uf = to_fix(ur);
                 }
                 warp_add_i(w.cl_nrm, cl, g * g, active);
                 warp_add_ll(w.cl_u, cl, uf, active);
@@ -920,22 +986,51 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
         }
         cluster.sync();
         LOOP_PROF(4)
-        if (my_t_root && !du_skip(c, w)) du_decide_one(w, my_t);
+        if (my_t_root && !skip) du_decide_one_hoisted(w, my_t);
         cluster.sync();
         LOOP_PROF(5)
         // ---- apply the step (this thread's rows), per-tree reset, bookkeeping ----
-        if (c.idx && w.act_n[2]) {
+        if (overflow) {
             if (gtid == 0) w.info[0] = 1;
         } else {
+            int a_fl[kClusterRowsPerThread], a_done[kClusterRowsPerThread], a_use[kClusterRowsPerThread];
+            double a_u[kClusterRowsPerThread], a_step[kClusterRowsPerThread];
+#pragma unroll
+            for (int q = 0; q < kClusterRowsPerThread; ++q) {
+                a_fl[q] = 0;
+                a_done[q] = 1;
+                a_use[q] = 0;
+                a_u[q] = 0.0;
+                a_step[q] = 0.0;
+                if (q < nq && my_r[q] >= 0) {
+                    a_fl[q] = w.cl_flag[my_cl[q]];
+                    a_done[q] = w.cl_done[my_cl[q]];
+                    a_step[q] = w.cl_step[my_cl[q]];
+                    a_u[q] = w.u[my_r[q]];
+                    a_use[q] = w.usage[my_r[q]];
+                }
+            }
+            int t_fl = 0, t_done = 0, t_arg = -1;
+            if (my_t >= 0 && my_t_has) {
+                t_fl = w.cl_flag[my_t_cl];
+                t_done = w.cl_done[my_t_cl];
+                t_arg = w.targ[my_t];
+            }
+            int b_iters = 0, b_s0 = 0, b_s1 = 0, b_s2 = 0;
+            if (gtid == 0) {
+                b_iters = w.info[1];
+                b_s0 = w.stall_ctr[0];
+                b_s1 = w.stall_ctr[1];
+                b_s2 = w.stall_ctr[2];
+            }
 #pragma unroll
             for (int q = 0; q < kClusterRowsPerThread; ++q) {
                 if (q >= nq) break;
-                const int r = my_r[q], cl = my_cl[q];
+                const int r = my_r[q];
                 if (r < 0) continue;
-                const int fl = w.cl_flag[cl];
-                const double ur = w.u[r];
-                if (fl & 1) w.best_u[r] = ur;
-                if (!w.cl_done[cl]) w.u[r] = fmax(0.0, ur + w.cl_step[cl] * (double)w.usage[r]);
+                const double ur = a_u[q];
+                if (a_fl[q] & 1) w.best_u[r] = ur;
+                if (!a_done[q]) w.u[r] = fmax(0.0, ur + a_step[q] * (double)a_use[q]);
                 w.usage[r] = 0;
             }
             if (my_t >= 0) {
@@ -945,17 +1040,17 @@ dual_loop_cluster_kernel(ColView c, AssocWork w, int iters, int greedy_every, in
                 w.cl_cost[t] = 0;
                 w.cl_nrm[t] = 0;
                 if (my_t_has) {
-                    const int cl = my_t_cl;
-                    if (w.cl_flag[cl] & 2) w.sel[t] = w.targ[t];
-                    w.tdone[t] = w.cl_done[cl];
+                    if (t_fl & 2) w.sel[t] = t_arg;
+                    w.tdone[t] = t_done;
                     w.tmin[t] = kKeyInf;
                     w.targ[t] = -1;
                 }
             }
             if (gtid == 0) {
-                w.info[1] += 1;
-                w.stall_ctr[0] = w.stall_ctr[2] ? 0 : w.stall_ctr[0] + 1;
-                if (w.stall_ctr[1] == 0 || w.stall_ctr[0] >= kStallStop) w.info[0] = 1;
+                w.info[1] = b_iters + 1;
+                const int s0 = b_s2 ? 0 : b_s0 + 1;
+                w.stall_ctr[0] = s0;
+                if (b_s1 == 0 || s0 >= kStallStop) w.info[0] = 1;
                 w.stall_ctr[1] = 0;
                 w.stall_ctr[2] = 0;
             }

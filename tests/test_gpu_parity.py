@@ -568,3 +568,40 @@ def test_associated_measurements_match_oracle(name):
         assert len(got) == len(orc.assoc), k
         for i, (a, b) in enumerate(zip(got, orc.assoc)):
             assert a == {(int(s), int(m)) for s, m in b}, (name, k, i, sorted(a ^ set(b))[:6])
+
+
+_LOOP_PROBE = r"""
+import json, sys
+sys.path.insert(0, %r)
+sys.path.insert(0, %r)
+import numpy as np
+from test_gpu_parity import _replay_tracker
+out = []
+for name, kw in (("cfg2", {}), ("cfg3_head", dict(maxTargets=1024, maxNodes=1 << 20, exactBudgetMs=30000))):
+    for k, g, pre, trk, nodes, hist, info in _replay_tracker(name, **kw):
+        out.append([name, k, info["dual_iters"], repr(info["lower_bound"]), repr(info["objective"]), info["certified"],
+                    [n.ID for n in nodes], hist])
+print("PROBE" + json.dumps(out))
+"""
+
+
+def test_cluster_loop_is_bit_identical_to_the_grid_loop():
+    """dual_loop_cluster_kernel (thread-block cluster, shared-memory resident columns, hoisted loads) against the
+    cooperative grid version of the same loop (MHT_NO_CLUSTER_LOOP=1, read once per process -> two subprocesses): same
+    iteration counts, bit-identical bounds and objectives, same tracks on every scan of cfg2 and cfg3_head."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = _LOOP_PROBE % (ROOT, os.path.join(ROOT, "tests"))
+    res = []
+    for extra in ({}, {"MHT_NO_CLUSTER_LOOP": "1"}):
+        env = dict(os.environ, **extra)
+        p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+        assert p.returncode == 0, p.stderr[-2000:]
+        line = [l for l in p.stdout.splitlines() if l.startswith("PROBE")][-1]
+        res.append(json.loads(line[5:]))
+    assert len(res[0]) == len(res[1]) > 0
+    for a, b in zip(res[0], res[1]):
+        assert a == b, (a[:6], b[:6])
