@@ -96,6 +96,7 @@ class ShardedTracker(Tracker):
         self.exchangeLog = []          # per scan: dict(n_cols_global, bytes_gathered, ms_exchange, ms_solve)
         self._buf = {}                 # persistent device buffers (grown geometrically, never per scan)
         self._solve_geometry = None    # (cap_cols, n_tree_slots, n_rows) of the workspace holding warm multipliers
+        self.globalTrackCount = 0      # tracks ever initiated on ANY rank: the next birth's Target.ID
 
     def _buffer(self, name, numel, dtype):
         t = self._buf.get(name)
@@ -112,6 +113,41 @@ class ShardedTracker(Tracker):
         for tgt in targets[lo:hi]:
             self.initiateTarget(Target(tgt.time, None, np.asarray(tgt.cartesianState(), dtype=np.float64), self.P_0,
                                        status=preinitializedTag))
+        self.globalTrackCount = len(targets)
+
+    def _births(self, new_targets):
+        """tracker.py:147-160 / 266-277 for a forest spread over ranks: a new target is accepted when NO rank holds a leaf
+        within mergeThreshold of it (one MIN all-reduce of the candidates' distances to the local leaves) and no target
+        accepted earlier in this scan is that close; accepted targets get the next GLOBAL id and go to rank id % world.
+        Every rank takes the same decisions from the same data."""
+        if not new_targets:
+            return
+        torch, dist = self._torch, self._dist
+        d = np.full(len(new_targets), np.inf)
+        if self.mergeThreshold > 0 and len(self._slots) > 0:
+            for k, tgt in enumerate(new_targets):
+                dk = C.c_double()
+                _lib.check(self._lib.mht_forest_min_leaf_distance(self._forest, float(tgt.x_0[0]), float(tgt.x_0[1]),
+                                                                  C.byref(dk)))
+                d[k] = dk.value
+        d_t = torch.from_numpy(d).to(self._device)
+        dist.all_reduce(d_t, op=dist.ReduceOp.MIN, group=self._group)
+        d = d_t.cpu().numpy()
+        accepted = []
+        threshold, self.mergeThreshold = self.mergeThreshold, 0.0       # decided here, globally
+        try:
+            for k, tgt in enumerate(new_targets):
+                p = np.asarray(tgt.x_0[0:2], dtype=np.float64)
+                if threshold > 0 and (d[k] < threshold or any(np.linalg.norm(p - q) < threshold for q in accepted)):
+                    continue
+                gid = self.globalTrackCount
+                self.globalTrackCount += 1
+                accepted.append(p)
+                if gid % self.world == self.rank:
+                    self.trackIdCounter = gid
+                    self.initiateTarget(tgt)
+        finally:
+            self.mergeThreshold = threshold
 
     def _agree(self, rc):
         """All ranks learn whether ANY rank failed before a collective is entered (a lone raise would hang the rest)."""
@@ -207,15 +243,13 @@ class ShardedTracker(Tracker):
         self.toc["Terminate"] = time.time() - t_term
         self.toc["N-Prune"] = info.ms_prune * 1e-3
         # births (tracker.py:266-277): the used mask is the OR over the shards; every rank runs the initiator on the
-        # same unused measurements and keeps the new targets whose global index falls to it (round robin)
+        # same unused measurements and takes the same global accept / id / owner decisions (_births)
         t_init = time.time()
         used_t = torch.from_numpy(used).to(self._device)
         dist.all_reduce(used_t, op=dist.ReduceOp.MAX, group=self._group)
         used = used_t.cpu().numpy()
         unused = scanList.filterUnused(used[:nMeas] == 0)
-        for k, initial_target in enumerate(self.initiator.processMeasurements(unused, [])):
-            if k % self.world == self.rank:
-                self.initiateTarget(initial_target)
+        self._births(self.initiator.processMeasurements(unused, []))
         self.toc["Init"] = time.time() - t_init
         self.toc["Total"] = time.time() - t_total
         for k, v in self.runtimeLog.items():
