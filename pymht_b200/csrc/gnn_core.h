@@ -231,7 +231,7 @@ struct Spec {
     double best;
     double c_d[kSpecCols];
     double r_d[kSpecRows];
-    int c_id[kSpecCols], c_pred[kSpecCols];
+    int c_id[kSpecCols], c_pred[kSpecCols], c_mrow[kSpecCols];   // c_mrow: the column's matched row, loaded with its potential
     int r_id[kSpecRows];
     int h_key[kSpecHash];
     short h_idx[kSpecHash];
@@ -271,15 +271,29 @@ GNN_HD void spec_search(W &w, const Graph &g, const State &st, Spec *sp, int s, 
     }
     for (int k = w.lane(); k < kSpecHash; k += w.nlanes()) sp->h_key[k] = -1;
     w.wsync();
-    int i = s;
+    // One scanned row per step, three dependent round trips to L2: {u, row_ptr} of the row -> {col, cost} of its edges ->
+    // {v, match_row} of their columns; everything else lives in the private table.
+    int i = s, mi = -1;
     double di = 0.0;
     while (true) {
-        const int mi = st.match_col[i];
         const double ui = st.u[i];
-        const double best = sp->best;
-        for (int e = g.row_ptr[i] + w.lane(); e < g.row_ptr[i + 1]; e += w.nlanes()) {
+        const int e0 = g.row_ptr[i], e1 = g.row_ptr[i + 1];
+        double best = sp->best;
+        if (i != s) {                                  // the row may give up its column and stay unassigned
+            double cand = di + (BIG - ui);
+            if (cand < di) cand = di;
+            if (cand < best) {
+                best = cand;
+                if (w.lane() == 0) {
+                    sp->best = cand;
+                    sp->end = g.n_cols + i;
+                }
+            }
+        }
+        for (int e = e0 + w.lane(); e < e1; e += w.nlanes()) {
             const int j = g.col[e];
             if (j == mi) continue;
+            const int mrow = st.match_row[j];
             double nd = di + ((g.cost[e] - ui) - st.v[j]);
             if (nd < di) nd = di;
             if (!(nd < best)) continue;
@@ -295,6 +309,7 @@ GNN_HD void spec_search(W &w, const Graph &g, const State &st, Spec *sp, int s, 
                         sp->c_id[k] = j;
                         sp->c_d[k] = nd;
                         sp->c_pred[k] = i;
+                        sp->c_mrow[k] = mrow;
                         sp->c_done[k] = 0;
                     } else {
                         sp->overflow = 1;
@@ -332,7 +347,7 @@ GNN_HD void spec_search(W &w, const Graph &g, const State &st, Spec *sp, int s, 
         const int js = w.wmin32(bd == m ? bj : kNoPred);
         const int ks = w.wmin32((bd == m && bj == js) ? bk : kNoPred);
         const double dmin = from_bits(m);
-        const int i2 = st.match_row[js];
+        const int i2 = sp->c_mrow[ks];
         const int nR = sp->nR;
         w.wsync();
         if (w.lane() == 0) {
@@ -346,17 +361,12 @@ GNN_HD void spec_search(W &w, const Graph &g, const State &st, Spec *sp, int s, 
                 sp->r_id[nR] = i2;
                 sp->r_d[nR] = dmin;
                 sp->nR = nR + 1;
-                double cand = dmin + (BIG - st.u[i2]);
-                if (cand < dmin) cand = dmin;
-                if (cand < sp->best) {
-                    sp->best = cand;
-                    sp->end = g.n_cols + i2;
-                }
             }
         }
         w.wsync();
         if (i2 < 0 || sp->overflow) break;
         i = i2;
+        mi = js;
         di = dmin;
     }
     if (w.lane() == 0 && sp->nC > kSpecCols) sp->nC = kSpecCols;
