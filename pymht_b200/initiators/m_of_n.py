@@ -67,18 +67,23 @@ def _merge_targets(targets):
 
 
 def _merge_similar_targets(initial_targets, threshold):
-    """m_of_n.py:126-145."""
+    """m_of_n.py:126-145, with the pairwise distances taken once (the reference recomputes a distance vector per target)."""
     if not initial_targets:
         return initial_targets
     pos = np.array([t.x_0[0:2] for t in initial_targets])
-    targets, used = [], set()
+    close_matrix = np.linalg.norm(pos[:, None, :] - pos[None, :, :], axis=2) < threshold
+    lonely = close_matrix.sum(axis=1) == 1            # nothing but the target itself within the threshold
+    targets, used = [], np.zeros(len(initial_targets), dtype=bool)
     for i, target in enumerate(initial_targets):
-        if i in used:
+        if used[i]:
             continue
-        close = np.where(np.linalg.norm(pos - pos[i], axis=1) < threshold)[0]
-        selected = [initial_targets[j] for j in close if j not in used]
+        if lonely[i]:
+            targets.append(target)
+            continue
+        close = np.flatnonzero(close_matrix[i])
+        selected = [initial_targets[j] for j in close if not used[j]]
         targets.append(_merge_targets(selected))
-        used.update(int(j) for j in close)
+        used[close] = True
     return targets
 
 
