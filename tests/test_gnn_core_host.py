@@ -68,3 +68,25 @@ def test_clustered_points_with_many_unassigned_rows(gnn_lib):
     for n_warps in (0, 16):
         got, stats = solve_sparse(gnn_lib, d, 40.0, n_warps)
         assert got == sorted(want), (n_warps, stats)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_ties_give_the_optimal_cardinality_and_cost(gnn_lib, seed):
+    """Degenerate costs (a handful of distinct integer values, many zero-reduced-cost alternating cycles): the assignment is
+    not unique, but its cardinality and total cost must be the reference formulation's optimum -- with and without the
+    speculative batches, which must also agree with each other run to run (the outcome depends on the data only)."""
+    rng = np.random.RandomState(100 + seed)
+    n1, n2 = rng.randint(20, 120), rng.randint(20, 120)
+    d = rng.randint(1, 5, size=(n1, n2)).astype(np.float64)
+    d[rng.uniform(size=(n1, n2)) > 0.08] = 1e9          # sparse gate
+    want = io.solve_gnn(d, 10.0)
+    cw = sum(d[i, j] for i, j in want)
+    outs = []
+    for n_warps in (0, 5, 64, 64):
+        got, stats = solve_sparse(gnn_lib, d, 10.0, n_warps)
+        assert len(set(j for _, j in got)) == len(got)                       # a matching
+        assert all(d[i, j] <= 10.0 for i, j in got)
+        assert len(got) == len(want), (n_warps, len(got), len(want), stats)
+        assert sum(d[i, j] for i, j in got) == cw, (n_warps, stats)
+        outs.append(got)
+    assert outs[2] == outs[3]
