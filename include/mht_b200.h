@@ -173,7 +173,8 @@ typedef struct mht_scan_info {
     int32_t rows_active;     /* measurement rows carrying a multiplier                                        */
     int32_t bb_iters;        /* subgradient iterations spent inside the branch & bound                        */
     int32_t open_components; /* components whose exact search did not finish (0 when certified)               */
-    int32_t reserved;
+    int32_t repaired_trees;  /* trees the final feasibility check moved to their miss hypothesis (lost a row to
+                                another track, or never got a primal solution); > 0 withdraws the certificate  */
 } mht_scan_info;
 
 int mht_forest_create(const mht_forest_config *cfg, mht_forest **out);
@@ -263,6 +264,12 @@ int mht_forest_history(mht_forest *f, int32_t slot, int32_t cap, int32_t *n, int
  * MHT_E_CAPACITY: *n_tracks holds the number of live tracks (cap_tracks too small) or the longest history (cap_len). */
 int mht_forest_histories(mht_forest *f, int32_t cap_tracks, int32_t cap_len, int32_t *n_tracks, int32_t *h_slot,
                          int32_t *h_len, int32_t *h_meas, double *h_x, double *h_cnllr, float *h_P);
+
+/* mht_forest_history for several slots in one call (the tracks that died in a scan, read before their slots are released):
+ * row i of the [n][cap_len] outputs belongs to h_slots[i] and holds h_len[i] nodes, oldest first.
+ * MHT_E_CAPACITY: h_len[0] holds the longest history. */
+int mht_forest_histories_of(mht_forest *f, int32_t n, const int32_t *h_slots, int32_t cap_len, int32_t *h_len,
+                            int32_t *h_meas, double *h_x, double *h_cnllr, float *h_P);
 
 /* Tracker.__associatedMeasurements__[i] (tracker.py:83,331-332,1226-1227): the (scanNumber, measurementNumber) pairs of
  * every node below the tree's current root (Target.getMeasurementSet, pyTarget.py:414-430), after the last scan's pruning.

@@ -50,7 +50,7 @@ class ScanInfo(C.Structure):
                 ("ms_assoc", C.c_float), ("ms_prune", C.c_float), ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("n_active", C.c_int64), ("max_component", C.c_int32), ("n_components", C.c_int32),
                 ("ms_dual", C.c_float), ("ms_exact", C.c_float), ("nnz_active", C.c_int64),
                 ("rows_active", C.c_int32), ("bb_iters", C.c_int32), ("open_components", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("repaired_trees", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -97,6 +97,7 @@ _SIGNATURES = {
     "mht_forest_windows": (C.c_int, [_vp, _i32, C.POINTER(_i32), _vp, _vp]),
     "mht_forest_history": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i32), _vp, _vp, _vp, _vp]),
     "mht_forest_histories": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i32), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mht_forest_histories_of": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mht_forest_measurement_set": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i32), _vp, _vp]),
     "mht_forest_min_leaf_distance": (C.c_int, [_vp, _dbl, _dbl, C.POINTER(_dbl)]),
     "mht_forest_leaves": (C.c_int, [_vp, _i32, _i64, C.POINTER(_i64), _vp, _vp, _vp]),

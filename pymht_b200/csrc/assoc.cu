@@ -2308,6 +2308,42 @@ __global__ void bb_state_kernel(AssocWork w) {
 }
 
 // single CTA: final objective and certificate
+// ---- last line of defence: the selection that leaves the solver is conflict free, whatever the parallel primal heuristics
+//      and the time-boxed exact search did.  Every selected column claims its rows (smallest tree index wins a row); a tree
+//      that lost a row falls back to its all-miss column (forest columns: the first column of the tree uses no row) and is
+//      counted in info[11], which also withdraws the certificate.  Three tiny launches per solve.
+__global__ void feas_reset_kernel(int R, int *claim) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R) claim[r] = 0x7fffffff;
+}
+__global__ void feas_claim_kernel(ColView c, AssocWork w, const int *tstart, int *claim) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= c.n_trees || tstart[t] < 0) return;
+    const int j = w.sel[t];
+    if (j < 0) return;
+    for (int k = 0; k < c.width; ++k) {
+        const int r = c.rows[(long long)k * c.stride + j];
+        if (r >= 0) atomicMin(&claim[r], t);
+    }
+}
+__global__ void feas_repair_kernel(ColView c, AssocWork w, const int *tstart, const int *claim) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= c.n_trees || tstart[t] < 0) return;
+    const int j = w.sel[t];
+    if (j < 0) return;
+    bool lost = false;
+    for (int k = 0; k < c.width; ++k) {
+        const int r = c.rows[(long long)k * c.stride + j];
+        if (r >= 0 && claim[r] != t) lost = true;
+    }
+    if (!lost) return;
+    const int j0 = tstart[t];
+    bool row_free = true;
+    for (int k = 0; k < c.width; ++k) row_free = row_free && c.rows[(long long)k * c.stride + j0] < 0;
+    if (row_free) w.sel[t] = j0;
+    atomicAdd(&w.info[11], 1);
+}
+
 __global__ void __launch_bounds__(1024, 1) final_objective_kernel(ColView c, AssocWork w, const int *tstart) {
     __shared__ long long ob;
     if (threadIdx.x == 0) ob = 0;
@@ -2749,6 +2785,9 @@ int assoc_solve(const ColView &c, AssocWork &w, int max_iters, int bb_budget, in
         }
         if (ev && ev->exact_end) MHT_CUDA(cudaEventRecord(ev->exact_end, s));
     }
+    count_launch(), feas_reset_kernel<<<(c.n_rows + 255) / 256, 256, 0, s>>>(c.n_rows, w.row_holder);
+    count_launch(), feas_claim_kernel<<<(c.n_trees + 255) / 256, 256, 0, s>>>(c, w, g_tstart, w.row_holder);
+    count_launch(), feas_repair_kernel<<<(c.n_trees + 255) / 256, 256, 0, s>>>(c, w, g_tstart, w.row_holder);
     count_launch(), final_objective_kernel<<<1, 1024, 0, s>>>(c, w, g_tstart);
     MHT_CUDA(cudaGetLastError());
     return MHT_OK;

@@ -112,7 +112,7 @@ struct AssocWork {
     // device status words
     int *info;                 // [kAssocInfo]: 0 all_done, 1 iters, 2 greedy_left, 3 n_cand, 4 n_comp,
                                // 5 open components, 6 cand_overflow, 7 n_clusters, 8 n_multi, 9 max_comp, 10 certified,
-                               // 11 trees without feasible incumbent, 12 n_active, 13 candidates before dominance,
+                               // 11 trees moved to their miss column (no primal solution, or lost a row in the final feasibility check), 12 n_active, 13 candidates before dominance,
                                // 14 iterations inside the exact search, 15 nnz of the columns the dual loop iterates on
     unsigned long long *bb_nodes;
     double *objective;         // [2]: lower bound, objective

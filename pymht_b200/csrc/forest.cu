@@ -1395,6 +1395,7 @@ static int forest_scan_impl(mht_forest *f, int64_t M, const double *d_z, mht_sca
         cudaEventElapsedTime(&info->ms_prune, f->ev[2], f->ev[4]);
         cudaEventElapsedTime(&info->ms_total, f->ev[0], f->ev[4]);
         info->open_components = st.assoc[5];
+        info->repaired_trees = st.assoc[11];
         info->nnz_active = st.assoc[15];
         info->bb_iters = st.assoc[14];
         info->rows_active = st.rows_active;
@@ -1874,6 +1875,36 @@ extern "C" int mht_forest_history(mht_forest *f, int32_t slot, int32_t cap, int3
         if (h_x) memcpy(h_x + 4 * i, o + 2, 32);
         if (h_P)
             for (int q = 0; q < 16; ++q) h_P[16 * i + q] = (float)o[8 + q];
+    }
+    return MHT_OK;
+}
+
+// mht_forest_history for SEVERAL slots in one call (the tracks that died in a scan: Tracker reads their histories before it
+// hands the slots back): row i of the [n][cap_len] outputs belongs to h_slots[i] and holds h_len[i] nodes, oldest first.
+extern "C" int mht_forest_histories_of(mht_forest *f, int32_t n, const int32_t *h_slots, int32_t cap_len, int32_t *h_len,
+                                       int32_t *h_meas, double *h_x, double *h_cnllr, float *h_P) {
+    if (!f || n < 0 || (n && (!h_slots || !h_len)) || cap_len < 1) {
+        set_error("mht_forest_histories_of: invalid argument");
+        return MHT_E_INVALID;
+    }
+    int need = 0;
+    for (int i = 0; i < n; ++i) {
+        int k = 0;
+        const int rc = mht_forest_history(f, h_slots[i], cap_len, &k, h_meas ? h_meas + (size_t)i * cap_len : nullptr,
+                                          h_x ? h_x + (size_t)4 * i * cap_len : nullptr,
+                                          h_cnllr ? h_cnllr + (size_t)i * cap_len : nullptr,
+                                          h_P ? h_P + (size_t)16 * i * cap_len : nullptr);
+        h_len[i] = k;
+        if (rc == MHT_E_CAPACITY) {
+            need = k > need ? k : need;
+            continue;
+        }
+        if (rc != MHT_OK) return rc;
+    }
+    if (need) {
+        h_len[0] = need;
+        set_error("mht_forest_histories_of: a history of %d nodes exceeds cap_len %d", need, cap_len);
+        return MHT_E_CAPACITY;
     }
     return MHT_OK;
 }

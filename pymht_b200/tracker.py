@@ -203,8 +203,10 @@ class Tracker:
             self.nNotOptimal += 1
             msg = ("Optim result NOT optimal (scan %d): objective %.6f, lower bound %.6f, gap %.3g; %d open "
                    "component(s), largest %d trees" % (len(self.__scanHistory__), info.objective, info.lower_bound,
-                                                       info.objective - info.lower_bound, info.n_components,
+                                                       info.objective - info.lower_bound, info.open_components,
                                                        info.max_component))
+            if info.repaired_trees:
+                msg += "; %d track(s) moved to their miss hypothesis by the final feasibility check" % info.repaired_trees
             if self.strict:
                 raise RuntimeError(msg)
             log.warning(msg)
@@ -272,14 +274,16 @@ class Tracker:
             x, P, cn, meas, status = x[order], P[order], cn[order], meas[order], status[order]
         self._last = (scanList, len(self.__scanHistory__), x, P, cn, meas, status)
         dead = np.flatnonzero(status[:k] != 0)
-        for i in dead:
-            # the library keeps the window records of a track that died this scan (mht_forest_history serves them
-            # from the host): read them now, then hand the slot back so that a later initiation can reuse it
+        hists = self._dead_histories([self._slots[i] for i in dead]) if (len(dead) and self._recycle_slots) else None
+        for q, i in enumerate(dead):
+            # the library keeps the window records of a track that died this scan (served from the host, no launch):
+            # they were read in ONE call above; now the slot goes back so that a later initiation can reuse it
             hist = None
             if self._recycle_slots:
-                hist = self._history(self._slots[i], prefetch=False)   # raw arrays (host copy, no launch); Targets stay lazy
+                hist = hists[q]                                        # raw arrays; Targets stay lazy
                 _lib.check(self._lib.mht_forest_release(self._forest, int(self._slots[i])))
-            self.__terminatedTargets__.append(self._make_node(int(i), self._slots[i], dead=True, hist=hist))
+            self.__terminatedTargets__.append(self._make_node(int(i), self._slots[i], dead=True, hist=hist,
+                                                              window=int(self.__targetWindowSize__[i])))
         if len(dead):
             keep = [i for i in range(k) if status[i] == 0]
             self._slots = [self._slots[i] for i in keep]
@@ -300,14 +304,15 @@ class Tracker:
         by_slot = dict(zip(slot[:n.value].tolist(), win[:n.value].tolist()))
         self.__targetWindowSize__ = [by_slot.get(s, w) for s, w in zip(self._slots, self.__targetWindowSize__)]
 
-    def _make_node(self, row, slot, dead=False, hist=None):
+    def _make_node(self, row, slot, dead=False, hist=None, window=None):
         scanList, scanNumber, x, P, cn, meas, status = self._last
         root = self._slot_info[slot]
         m = int(meas[row])
         return Target(scanList.time, scanNumber, x[row].copy(), P[row].copy(), ID=root.ID, P_d=root.P_d,
                       measurementNumber=m, measurement=(np.asarray(scanList.measurements)[m - 1] if m > 0 else None),
                       cumulativeNLLR=float(cn[row]), status=STATUS_TAGS[int(status[row])],
-                      parent_loader=self._make_parent_loader(slot, dead, self._window_of(slot), hist))
+                      parent_loader=self._make_parent_loader(slot, dead, self._window_of(slot) if window is None else window,
+                                                             hist))
 
     def _prefetch_histories(self):
         """Histories of ALL live tracks in a handful of launches (mht_forest_histories); valid until the next scan."""
@@ -357,6 +362,24 @@ class Tracker:
             _lib.check(rc)
             k = n.value
             return meas[:k], x[:k], cn[:k], P[:k]
+
+    def _dead_histories(self, slots):
+        """(meas, x, cnllr, P) of every given slot with one library call (mht_forest_histories_of)."""
+        n, cap = len(slots), 64
+        sl = np.asarray(slots, dtype=np.int32)
+        while True:
+            ln = np.zeros(n, dtype=np.int32)
+            meas = np.zeros((n, cap), dtype=np.int32)
+            x = np.zeros((n, cap, 4), dtype=np.float64)
+            cn = np.zeros((n, cap), dtype=np.float64)
+            P = np.zeros((n, cap, 4, 4), dtype=np.float32)
+            rc = self._lib.mht_forest_histories_of(self._forest, n, _lib.ptr(sl), cap, _lib.ptr(ln), _lib.ptr(meas),
+                                                   _lib.ptr(x), _lib.ptr(cn), _lib.ptr(P))
+            if rc == _lib.MHT_E_CAPACITY:
+                cap = int(ln[0]) + 8
+                continue
+            _lib.check(rc)
+            return [(meas[i, :ln[i]], x[i, :ln[i]], cn[i, :ln[i]], P[i, :ln[i]]) for i in range(n)]
 
     def _window_of(self, slot):
         try:

@@ -306,7 +306,7 @@ def test_large_random_forest_properties():
     """Full-size property checks (no oracle at this size): every track selects exactly one leaf, no
     measurement is shared between selected hypotheses' current-scan associations, the bound brackets
     the objective, leaves stay sorted, and capacity errors are reported, not hidden."""
-    from pymht_b200.tracker import Tracker
+    from pymht_b200.tracker import Tracker, backtrackMeasurementNumbers
     from pymht_b200.models import pv
     import pymht_b200.utils.simulator as sim
     sim.seed_simulator(7)
@@ -323,7 +323,13 @@ def test_large_random_forest_properties():
         nodes = trk.getTrackNodes()
         used = [n.measurementNumber for n in nodes if n.measurementNumber > 0]
         assert len(used) == len(set(used)), "a measurement was assigned to two tracks"
-        assert info["lower_bound"] <= info["objective"] + 1e-6
+        hist = backtrackMeasurementNumbers(nodes)
+        for back in range(1, 8):          # ... nor a measurement of any earlier scan of the window
+            old = [h[-back] for h in hist if len(h) >= back and h[-back] > 0]
+            assert len(old) == len(set(old)), ("two tracks share a measurement %d scans back" % (back - 1), info)
+        assert info["lower_bound"] <= info["objective"] + 1e-6, info
+        if info["repaired_trees"]:
+            print("scan with %d repaired trees:" % info["repaired_trees"], info)
         assert len(nodes) + info["n_dead"] == info["n_trees"]
         assert info["n_children"] == info["n_parents"] + info["n_pairs"]
     trk.close()
