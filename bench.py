@@ -421,9 +421,12 @@ def main():
                     "gap_mean": float(np.mean(gaps)), "gap_max": float(np.max(gaps)),
                     "gap_rel_mean": float(np.mean([g / max(abs(d["lower_bound"]), 1e-9) for g, d in zip(gaps, timed)])),
                     "open_components_mean": float(np.mean([d["open_components"] for d in timed])),
+                    "repaired_trees": int(sum(d.get("repaired_trees", 0) for d in timed)),
                     "note": "certified = the exact search proved the selection optimal; otherwise a feasible "
                             "selection with the stated gap to the Lagrangian lower bound (the reference's CBC would "
-                            "warn 'NOT optimal' under a time limit, tracker.py:1201-1204)"},
+                            "warn 'NOT optimal' under a time limit, tracker.py:1201-1204); repaired_trees = tracks the "
+                            "final feasibility check of the selection had to move to their miss hypothesis (0 = every "
+                            "selection left the solver conflict free)"},
             "scan_stats": {k: float(np.mean([d[k] for d in timed])) for k in
                            ("n_trees", "n_parents", "n_children", "n_pairs", "n_clusters", "n_multi_clusters", "dual_iters",
                             "n_candidates", "bb_nodes", "bb_iters", "certified", "lower_bound", "objective", "n_active",
