@@ -149,3 +149,59 @@ def test_shard_bounds_cover_everything():
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def _births_worker(rank, world, port, out):
+    """ShardedTracker._births on a stand-in forest (gloo): each rank only knows the leaves it holds; the accept / id / owner
+    decisions must come out the same on every rank and follow tracker.py:147-160 for the union of the leaves."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ctypes as C
+    from pymht_b200 import sharded as sh
+    from pymht_b200.pyTarget import Target
+
+    leaves = [np.array([[0.0, 0.0], [100.0, 0.0]]), np.array([[0.0, 100.0]])][rank]     # rank 0 holds two leaves, rank 1 one
+
+    class FakeLib:
+        def mht_forest_min_leaf_distance(self, forest, x, y, ref):
+            ref._obj.value = float(np.min(np.linalg.norm(leaves - np.array([x, y]), axis=1)))
+            return 0
+
+    class Stub:
+        pass
+    trk = Stub()
+    trk._torch, trk._dist, trk._group, trk._device = torch, dist, None, torch.device("cpu")
+    trk.rank, trk.world = rank, world
+    trk._lib, trk._forest, trk._slots = FakeLib(), None, list(range(len(leaves)))
+    trk.mergeThreshold, trk.globalTrackCount, trk.trackIdCounter = 25.0, 3, 0
+    born = []
+    trk.initiateTarget = lambda tgt: born.append((trk.trackIdCounter, float(tgt.x_0[0]), float(tgt.x_0[1])))
+    P = np.eye(4)
+    cands = [Target(0.0, None, np.array([x, y, 0.0, 0.0]), P) for x, y in
+             [(10.0, 0.0),      # 10 m from a leaf of rank 0 -> rejected everywhere
+              (0.0, 90.0),      # 10 m from the leaf of rank 1 -> rejected everywhere
+              (300.0, 300.0),   # free -> id 3, rank 3 % 2 = 1
+              (310.0, 300.0),   # 10 m from the target accepted just before -> rejected
+              (500.0, 0.0),     # free -> id 4, rank 0
+              (0.0, 500.0)]]    # free -> id 5, rank 1
+    sh.ShardedTracker._births(trk, cands)
+    out.put((rank, born, trk.globalTrackCount, trk.mergeThreshold))
+    dist.destroy_process_group()
+
+
+def test_sharded_births_decide_globally_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_births_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, born0, n0, thr0), (_, born1, n1, thr1) = res
+    assert n0 == n1 == 6 and thr0 == thr1 == 25.0                 # three accepted; the threshold is restored
+    assert born0 == [(4, 500.0, 0.0)]
+    assert born1 == [(3, 300.0, 300.0), (5, 0.0, 500.0)]
