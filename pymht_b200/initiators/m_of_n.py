@@ -98,9 +98,10 @@ class Initiator:
         self.last_timestamp = None
         self.merge_threshold = mergeThreshold
         self._lib = _lib.load()
-        self._gnn = C_void()
+        self._gnn = C.c_void_p()
         self._cap = (0, 0, 0)
-        self._ensure(int(kwargs.get("maxMeasurements", 4096)), int(kwargs.get("maxMeasurements", 4096)))
+        n0 = int(kwargs.get("maxMeasurements", 4096))     # initial capacity only: the buffers grow with the problem
+        self._ensure(n0, n0)
         self._state = np.zeros((0, 4), dtype=np.float32)
         self._cov = np.zeros((0, 4, 4), dtype=np.float32)
         self._m = np.zeros(0, dtype=np.int64)
@@ -121,11 +122,17 @@ class Initiator:
     def initiators(self):
         return [Measurement(v, self._init_time) for v in self._init_z]
 
+    def close(self):
+        """Free the device buffers (also done when the object is collected)."""
+        gnn = getattr(self, "_gnn", None)
+        if gnn is not None and gnn.value:
+            self._lib.mht_gnn_destroy(gnn)
+            self._gnn = C.c_void_p()
+            self._cap = (0, 0, 0)
+
     def __del__(self):
         try:
-            if getattr(self, "_gnn", None) is not None and self._gnn.value:
-                self._lib.mht_gnn_destroy(self._gnn)
-                self._gnn = C_void()
+            self.close()
         except Exception:
             pass
 
@@ -142,7 +149,7 @@ class Initiator:
     def _create(self, r, c, e):
         if self._gnn.value:
             self._lib.mht_gnn_destroy(self._gnn)
-            self._gnn = C_void()
+            self._gnn = C.c_void_p()
         _lib.check(self._lib.mht_gnn_create(r, c, e, C.byref(self._gnn)))
         self._cap = (r, c, e)
 
@@ -286,6 +293,3 @@ class Initiator:
         self._n = np.concatenate((self._n, np.zeros(nK, dtype=np.int64)))
         self._midx = np.concatenate((self._midx, -np.ones(nK, dtype=np.int64)))
 
-
-def C_void():
-    return C.c_void_p()

@@ -131,6 +131,9 @@ class Tracker:
         if self._forest is not None:
             self._lib.mht_forest_destroy(self._forest)
             self._forest = None
+        closer = getattr(getattr(self, "initiator", None), "close", None)
+        if callable(closer):
+            closer()
 
     def __del__(self):
         try:

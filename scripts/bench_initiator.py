@@ -92,7 +92,7 @@ def main():
     run_gpu(lists[:2])                                      # warm-up: module load, buffers
     _, full = run_gpu(lists)
     sub = [MeasurementList(ml.time, np.asarray(ml.measurements)[:args.sample]) for ml in lists[:args.ref_scans]]
-    ini_s, gpu_sub = run_gpu(sub)
+    _, gpu_sub = run_gpu(sub)
     ref_rows, ref_out = run_reference(sub)
     # same inputs, same results?
     from pymht_b200.initiators import m_of_n
