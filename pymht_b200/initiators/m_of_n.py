@@ -32,6 +32,7 @@ CONFIRMED, PRELIMINARY, DEAD = 1, 0, -1
 R_AIS_LOW = np.float32(3.0 ** 2)          # models/ais.py:9-13, R(False), used by compareSimilarity (:198)
 
 log = logging.getLogger(__name__)
+_void_p = C.c_void_p        # Initiator.__init__ has a parameter called C (the observation matrix), like the reference
 
 
 class PreliminaryTrack:
@@ -98,7 +99,7 @@ class Initiator:
         self.last_timestamp = None
         self.merge_threshold = mergeThreshold
         self._lib = _lib.load()
-        self._gnn = C.c_void_p()
+        self._gnn = _void_p()
         self._cap = (0, 0, 0)
         n0 = int(kwargs.get("maxMeasurements", 4096))     # initial capacity only: the buffers grow with the problem
         self._ensure(n0, n0)
@@ -127,7 +128,7 @@ class Initiator:
         gnn = getattr(self, "_gnn", None)
         if gnn is not None and gnn.value:
             self._lib.mht_gnn_destroy(gnn)
-            self._gnn = C.c_void_p()
+            self._gnn = _void_p()
             self._cap = (0, 0, 0)
 
     def __del__(self):
@@ -149,7 +150,7 @@ class Initiator:
     def _create(self, r, c, e):
         if self._gnn.value:
             self._lib.mht_gnn_destroy(self._gnn)
-            self._gnn = C.c_void_p()
+            self._gnn = _void_p()
         _lib.check(self._lib.mht_gnn_create(r, c, e, C.byref(self._gnn)))
         self._cap = (r, c, e)
 

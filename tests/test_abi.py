@@ -41,6 +41,14 @@ def test_no_cpu_fallback_without_device():
     with pytest.raises(_lib.MhtError) as e:
         Tracker(pv, 2.5, 1e-4, 1e-9, initiator=None)
     assert e.value.code == _lib.MHT_E_NODEVICE
+    # the M-of-N initiator has no CPU path either (its constructor creates the device buffers)
+    from pymht_b200.initiators import m_of_n
+    with pytest.raises(_lib.MhtError) as e:
+        m_of_n.Initiator(2, 3, 20, pv.C_RADAR, pv.R_RADAR(), 25.0)
+    assert e.value.code == _lib.MHT_E_NODEVICE
+    with pytest.raises(_lib.MhtError) as e:
+        Tracker(pv, 2.5, 1e-4, 1e-9)              # default: initiator live, like the reference
+    assert e.value.code == _lib.MHT_E_NODEVICE
 
 
 def test_product_never_imports_oracle():
