@@ -1879,6 +1879,12 @@ __global__ void __launch_bounds__(32) branch_bound_kernel(ColView c, AssocWork w
                 pos[depth] = 0;
             }
         }
+        if (exhausted)   // out of budget in the middle of a branch: give the rows of the partial assignment back
+            for (int d = 0; d <= depth; ++d)
+                for (int kk = 0; kk < c.width; ++kk) {
+                    const int r = c.rows[(long long)kk * c.stride + chosen[d]];
+                    if (r >= 0) w.row_taken[r] = 0;
+                }
         for (int i = 0; i < k; ++i) w.sel[trees[i]] = bestsel[i];
         atomicAdd(w.bb_nodes, nodes);
         if (!exhausted) w.bbw.comp_state[comp] = 1;
