@@ -30,9 +30,10 @@ for rep in range(reps):
             conflicts += len(used) - len(set(used))
         flag = info["lower_bound"] > info["objective"] + 1e-6
         bad += flag
-        print("rep %d scan %d: lb %.6f obj %.6f cert %d open %d comps %d maxc %d nodes %d iters %d cand %d conflicts %d %s" % (
-            rep, k + 1, info["lower_bound"], info["objective"], info["certified"], info["open_components"],
-            info["n_components"], info["max_component"], info["bb_nodes"], info["dual_iters"], info["n_candidates"], conflicts,
-            "<-- LB > OBJ" if flag else ""), flush=True)
+        if flag or conflicts or info["repaired_trees"] or rep == 0:
+            print("rep %d scan %d: lb %.6f obj %.6f cert %d open %d comps %d maxc %d nodes %d iters %d cand %d conflicts %d repaired %d %s" % (
+                rep, k + 1, info["lower_bound"], info["objective"], info["certified"], info["open_components"],
+                info["n_components"], info["max_component"], info["bb_nodes"], info["dual_iters"], info["n_candidates"], conflicts,
+                info["repaired_trees"], "<-- LB > OBJ" if flag else ""), flush=True)
     trk.close()
 print("bad scans:", bad)
