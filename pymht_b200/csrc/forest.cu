@@ -1558,6 +1558,9 @@ extern "C" int mht_forest_create(const mht_forest_config *cfg, mht_forest **out)
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(forest_emit_kernel<MHT_MAX_WINDOW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)emit_smem_bytes(MHT_MAX_WINDOW));
+    // the arena starts from zeros whatever a previous owner of the memory left in it: a freshly mapped allocation is zero
+    // filled by the driver, a recycled one is not, and nothing here may depend on which of the two it got
+    if (e == cudaSuccess) e = cudaMemsetAsync(f->arena, 0, (size_t)f->bytes, f->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(f->ts.alive, 0, sizeof(int) * T, f->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(f->rows[0], 0xff, sizeof(int) * (size_t)f->W * f->cap_nodes, f->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);

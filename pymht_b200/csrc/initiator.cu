@@ -521,6 +521,7 @@ extern "C" int mht_gnn_create(int64_t max_rows, int64_t max_cols, int64_t max_ed
         return MHT_E_CUDA;
     }
     gnn_carve(h);
+    cudaMemset(h->arena, 0, (size_t)h->bytes);
     h->stream = 0;
     if (cudaMallocHost(&h->hdr_h, 64) != cudaSuccess || cudaEventCreate(&h->ev[0]) != cudaSuccess ||
         cudaEventCreate(&h->ev[1]) != cudaSuccess || cudaEventCreate(&h->ev[2]) != cudaSuccess) {
