@@ -128,3 +128,23 @@ def test_initiator_oracle_vs_reference_fixture(name):
         assert np.allclose(st, g[pre + "pt_state"], rtol=1e-6, atol=1e-6)
         assert np.array_equal(np.array([[p.m, p.n] for p in o.preliminary_tracks]).reshape(-1, 2), g[pre + "pt_mn"])
         assert np.array_equal(o.initiators, g[pre + "initiators"])
+
+
+def test_host_merge_of_similar_targets_equals_oracle():
+    """pymht_b200.initiators.m_of_n._merge_similar_targets (host part of the product's initiator: pairwise distances taken
+    once) against the oracle's restatement of m_of_n.py:117-145 on random clustered initial targets."""
+    from oracle.initiator_oracle import InitiatorOracle
+    from pymht_b200.initiators import m_of_n
+    from pymht_b200.pyTarget import Target
+    rng = np.random.RandomState(0)
+    for trial in range(100):
+        k = rng.randint(1, 40)
+        cent = rng.uniform(0, 200, (6, 2))
+        x = np.hstack([cent[rng.randint(0, 6, k)] + rng.normal(scale=12, size=(k, 2)), rng.normal(size=(k, 2))])
+        tg = [Target(0.0, None, x[i], np.eye(4) * (i + 1), measurement=x[i, :2]) for i in range(k)]
+        got = m_of_n._merge_similar_targets(tg, 25.0)
+        o = InitiatorOracle(2, 3, 20, np.eye(2, 4), np.eye(2), 25.0)
+        want = o._merge([(x[i], np.eye(4) * (i + 1), x[i, :2], i) for i in range(k)])
+        assert len(got) == len(want)
+        for g_, w_ in zip(got, want):
+            assert np.allclose(g_.x_0, w_[0]) and np.allclose(g_.P_0, w_[1])
