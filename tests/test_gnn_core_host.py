@@ -90,3 +90,39 @@ def test_ties_give_the_optimal_cardinality_and_cost(gnn_lib, seed):
         assert sum(d[i, j] for i, j in got) == cw, (n_warps, stats)
         outs.append(got)
     assert outs[2] == outs[3]
+
+
+def _brute_force(d, gate):
+    """All matchings of the gated pairs of a tiny problem: (maximum cardinality, then minimum total cost)."""
+    n1, n2 = d.shape
+    best = (0, 0.0)
+
+    def rec(i, used, card, cost):
+        nonlocal best
+        if i == n1:
+            if card > best[0] or (card == best[0] and cost < best[1] - 1e-12):
+                best = (card, cost)
+            return
+        rec(i + 1, used, card, cost)
+        for j in range(n2):
+            if not (used >> j) & 1 and d[i, j] <= gate:
+                rec(i + 1, used | (1 << j), card + 1, cost + d[i, j])
+    rec(0, 0, 0, 0.0)
+    return best
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_tiny_problems_against_brute_force(gnn_lib, seed):
+    """Independent of SciPy and of the reference's padding construction: on problems small enough to enumerate, the core's
+    assignment has the maximum cardinality and, among those, the minimum cost -- what m_of_n.py:24-104 computes."""
+    rng = np.random.RandomState(900 + seed)
+    n1, n2 = rng.randint(1, 7), rng.randint(1, 7)
+    d = rng.uniform(0, 10, (n1, n2))
+    gate = 6.0
+    card, cost = _brute_force(d, gate)
+    for n_warps in (0, 3):
+        got, stats = solve_sparse(gnn_lib, d, gate, n_warps)
+        assert len(got) == card, (n_warps, got, card)
+        assert abs(sum(d[i, j] for i, j in got) - cost) < 1e-9, (n_warps, got, cost)
+    want = io.solve_gnn(d, gate)                      # and the oracle's restatement agrees with the enumeration too
+    assert len(want) == card and abs(sum(d[i, j] for i, j in want) - cost) < 1e-9
